@@ -1,0 +1,289 @@
+"""Parity of the CUDA path against the oracle and the reference's golden streams.
+Every test here calls through the C ABI (via zipnn_b200.ZipNN or ctypes directly)."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_stream, load_manifest
+from golden_inputs import make_input, raw_bytes
+from oracle import oracle as O
+from zipnn_b200 import ZipNN, _native
+
+pytestmark = pytest.mark.gpu
+CASES = load_manifest()
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def _u8(t):
+    return t.detach().contiguous().reshape(-1).view(torch.uint8)
+
+
+# ------------------------------------------------------------------ golden streams
+@pytest.mark.parametrize("rec", CASES, ids=[c["name"] for c in CASES])
+def test_golden_compress_and_decompress(rec):
+    data = make_input(rec["input"])
+    raw = raw_bytes(data)
+    if sha(raw) != rec["input_sha256"]:
+        pytest.skip("input generator drifted on this machine")
+    torch_fmt = rec["ctor"]["input_format"] == "torch"
+    # --- device-resident: CUDA tensor in, CUDA stream out
+    z = ZipNN(**rec["ctor"])
+    dev_in = data.cuda() if torch_fmt else torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    keep = _u8(dev_in).clone()
+    stream = z.compress(dev_in)
+    assert stream.is_cuda and stream.dtype == torch.uint8
+    assert torch.equal(_u8(dev_in), keep), "compress must not modify its input"
+    sbytes = stream.cpu().numpy().tobytes()
+    assert len(sbytes) == rec["stream_len"]
+    assert sha(sbytes) == rec["stream_sha256"]
+    gold = golden_stream(rec)
+    if gold is not None:
+        assert sbytes == gold
+    back = ZipNN(**rec["ctor"]).decompress(stream)
+    assert back.is_cuda
+    if torch_fmt:
+        assert back.dtype == data.dtype and tuple(back.shape) == tuple(data.shape)
+    assert _u8(back).cpu().numpy().tobytes() == raw
+    # --- host buffers: the reference's own calling convention
+    zh = ZipNN(**rec["ctor"])
+    hstream = zh.compress(data.clone() if torch_fmt else raw)
+    assert bytes(hstream) == sbytes
+    hback = ZipNN(**rec["ctor"]).decompress(bytes(hstream))
+    if torch_fmt:
+        assert not hback.is_cuda and hback.dtype == data.dtype and tuple(hback.shape) == tuple(data.shape)
+        assert raw_bytes(hback) == raw
+    else:
+        assert bytes(hback) == raw
+
+
+def test_decodes_committed_reference_streams_directly():
+    """Decode bytes the REFERENCE wrote (tests/golden/*.znn), not bytes we produced."""
+    n = 0
+    for rec in CASES:
+        gold = golden_stream(rec)
+        if gold is None:
+            continue
+        data = make_input(rec["input"])
+        raw = raw_bytes(data)
+        if sha(raw) != rec["input_sha256"]:
+            continue
+        out = ZipNN(**rec["ctor"]).decompress(torch.frombuffer(bytearray(gold), dtype=torch.uint8).cuda())
+        assert _u8(out).cpu().numpy().tobytes() == raw
+        n += 1
+    assert n >= 10
+
+
+# ------------------------------------------------------------------ oracle on seeded inputs
+def _plane_inputs(rng, kind, n):
+    if kind == "gauss16":
+        x = (rng.standard_normal(n // 2 + 1) * 0.02).astype(np.float32)
+        return np.ascontiguousarray((x.view(np.uint32) >> 16).astype(np.uint16).view(np.uint8)[:n])
+    if kind == "gauss32":
+        x = (rng.standard_normal(n // 4 + 1) * 0.02).astype(np.float32)
+        return np.ascontiguousarray(x.view(np.uint8)[:n])
+    if kind == "bytes":
+        return rng.integers(0, 256, n, dtype=np.uint8)
+    if kind == "zeros":
+        return np.zeros(n, dtype=np.uint8)
+    if kind == "few":
+        return rng.choice(6, n, p=[.5, .25, .12, .06, .04, .03]).astype(np.uint8)
+    if kind == "skew":
+        k = int(rng.integers(130, 256))
+        return (255 - rng.choice(k, n, p=rng.dirichlet(np.ones(k) * 0.3))).astype(np.uint8)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("G,bits", [(1, 0), (2, 1), (2, 0), (4, 1), (4, 0)])
+def test_cabi_matches_oracle_on_seeded_inputs(G, bits):
+    rng = np.random.default_rng(100 + 10 * G + bits)
+    L = _native.lib()
+    bm = 220 if G == 4 else 10
+    kinds = ["gauss16", "gauss32", "bytes", "zeros", "few", "skew"]
+    for it in range(36):
+        chunk = 131072 if G == 1 else int(rng.choice([262144, 262144, 65536, 4096, 1024]))
+        sizes = [G, 2 * G, 12 * G, 13 * G, chunk - G, chunk, chunk + G, 3 * chunk + 5 * G, 64, 4096,
+                 int(rng.integers(1, 40000)) * G, int(rng.integers(1, 6 * chunk // G + 2)) * G]
+        n = int(sizes[it % len(sizes)])
+        data = _plane_inputs(rng, kinds[it % len(kinds)], n)
+        hdr = bytearray(32 + (it % 5))
+        hdr[0:2] = b"ZN"
+        want = O.zipnn_compress(hdr, data, G, bits, bm, chunk, 0.95, threads=4)
+        d_in = torch.from_numpy(data.copy()).cuda()
+        bound = _native.compress_bound(n, G, chunk, len(hdr))
+        d_out = torch.zeros(bound, dtype=torch.uint8, device="cuda")
+        ws = torch.empty(_native.compress_workspace_size(n, G, chunk), dtype=torch.uint8, device="cuda")
+        out_len = C.c_size_t(0)
+        hbuf = (C.c_char * len(hdr)).from_buffer_copy(bytes(hdr))
+        st = L.zipnn_b200_compress(d_in.data_ptr(), n, hbuf, len(hdr), G, bits, bm, chunk, 0.95, d_out.data_ptr(), bound,
+                                   C.byref(out_len), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        assert st == 0, st
+        got = d_out[: out_len.value].cpu().numpy()
+        assert out_len.value == want.size, (it, n, chunk, out_len.value, want.size)
+        assert np.array_equal(got, want), (it, n, chunk)
+        assert np.array_equal(d_in.cpu().numpy(), data)
+        # decode the ORACLE's stream with the CUDA path
+        body = torch.from_numpy(want[len(hdr):].copy()).cuda()
+        d_dec = torch.zeros(n + 16, dtype=torch.uint8, device="cuda")
+        ws2 = torch.empty(_native.decompress_workspace_size(n, G, chunk), dtype=torch.uint8, device="cuda")
+        st = L.zipnn_b200_decompress(body.data_ptr(), body.numel(), G, bits, bm, chunk, n, d_dec.data_ptr(), ws2.data_ptr(),
+                                     ws2.numel(), torch.cuda.current_stream().cuda_stream, 1)
+        assert st == 0, (st, it, n, chunk)
+        assert np.array_equal(d_dec[:n].cpu().numpy(), data), (it, n, chunk)
+        assert int(d_dec[n:].sum()) == 0, "wrote past the end of the output"
+
+
+@pytest.mark.parametrize("G,bits", [(1, 0), (2, 1), (2, 0), (4, 1)])
+def test_split_regroup_match_oracle(G, bits):
+    rng = np.random.default_rng(7 + G)
+    L = _native.lib()
+    for n in [G, 16 * G, 16 * G + G, 4096 * G, 100003 * G, 262144]:
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+        want = O.split_chunk(data, G, bits)
+        stride = ((n + G - 1) // G + 15) // 16 * 16
+        d_in = torch.from_numpy(data.copy()).cuda()
+        planes = torch.zeros(G * stride, dtype=torch.uint8, device="cuda")
+        assert L.zipnn_b200_split(d_in.data_ptr(), n, G, bits, planes.data_ptr(), stride, torch.cuda.current_stream().cuda_stream) == 0
+        host = planes.cpu().numpy()
+        for g in range(G):
+            assert np.array_equal(host[g * stride: g * stride + want[g].size], want[g]), (n, g)
+        back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        assert L.zipnn_b200_regroup(planes.data_ptr(), stride, n, G, bits, back.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+        assert np.array_equal(back.cpu().numpy(), data)
+        assert np.array_equal(d_in.cpu().numpy(), data)
+
+
+# ------------------------------------------------------------------ edge cases + errors
+def test_empty_and_tiny_tensors():
+    for dt in (torch.bfloat16, torch.float32, torch.float16, torch.float8_e4m3fn):
+        for n in (0, 1, 2, 3, 7):
+            t = (torch.randn(n) * 0.02).to(dt)
+            z = ZipNN(input_format="torch")
+            s = z.compress(t.cuda())
+            plan = ZipNN(input_format="torch").plan(t)
+            want = O.zipnn_compress(plan["header"], np.frombuffer(raw_bytes(t), dtype=np.uint8), plan["num_buf"], plan["bit_reorder"],
+                                    plan["byte_reorder"], plan["chunk"], plan["threshold"])
+            assert s.cpu().numpy().tobytes() == want.tobytes(), (dt, n)
+            back = ZipNN(input_format="torch").decompress(s)
+            assert back.dtype == dt and back.numel() == n
+            assert raw_bytes(back.cpu()) == raw_bytes(t)
+
+
+def test_unaligned_views_and_noncontiguous_inputs():
+    base = (torch.randn(300001) * 0.02).to(torch.bfloat16).cuda()
+    for t in (base[1:], base[3:70001], base.reshape(-1)[::2]):
+        s = ZipNN(input_format="torch").compress(t)
+        back = ZipNN(input_format="torch").decompress(s)
+        assert torch.equal(back.view(torch.int16), t.contiguous().view(torch.int16))
+    # stream held at an odd offset inside a larger buffer
+    s = ZipNN(input_format="torch").compress(base)
+    big = torch.zeros(s.numel() + 13, dtype=torch.uint8, device="cuda")
+    big[5: 5 + s.numel()] = s
+    back = ZipNN(input_format="torch").decompress(big[5: 5 + s.numel()])
+    assert torch.equal(back.view(torch.int16), base.view(torch.int16))
+
+
+def test_corrupt_streams_are_rejected():
+    t = (torch.randn(200000) * 0.02).to(torch.bfloat16).cuda()
+    s = ZipNN(input_format="torch").compress(t).clone()
+    with pytest.raises(ValueError):
+        bad = s.clone()
+        bad[0] = 0x41
+        ZipNN(input_format="torch").decompress(bad)
+    hdr_len = 32 + 1 + 4  # 1-D shape, 4-byte dim
+    bad = s.clone()
+    bad[hdr_len + 1] = 7  # type byte of (group 1, chunk 0) out of range
+    with pytest.raises(RuntimeError):
+        ZipNN(input_format="torch").decompress(bad)
+    bad = s.clone()
+    bad[-1] = 0  # last stream loses its end mark
+    with pytest.raises(RuntimeError):
+        ZipNN(input_format="torch").decompress(bad)
+    bad = s.clone()
+    K = 2
+    bad[hdr_len + 2 * K + 8 * K + 3] ^= 0x40  # cumulative size of group 1 scrambled
+    with pytest.raises(RuntimeError):
+        ZipNN(input_format="torch").decompress(bad)
+    # random bit flips inside the Huffman payload: either a clean error or wrong data, never a crash
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        bad = s.clone()
+        pos = int(rng.integers(s.numel() // 2 + 64, s.numel()))
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            ZipNN(input_format="torch").decompress(bad)
+        except RuntimeError:
+            pass
+    torch.cuda.synchronize()
+
+
+def test_reference_stress_sizes_round_trip():
+    """The reference's own stress sizes (tests/simple_stress_tests.py:19-70): bf16 rand*2-1 and
+    random bytes at 255/256/257/511/512/513/1024 KiB and about 1 and 2 MiB."""
+    g = torch.Generator().manual_seed(0)
+    for kib in (255, 256, 257, 511, 512, 513, 1024, 1025, 2049):
+        n = kib * 1024 // 2
+        t = (torch.rand(n, generator=g) * 2 - 1).to(torch.bfloat16)
+        s = ZipNN(input_format="torch").compress(t.cuda())
+        plan = ZipNN(input_format="torch").plan(t)
+        want = O.zipnn_compress(plan["header"], np.frombuffer(raw_bytes(t), dtype=np.uint8), 2, 1, 10, 262144, 0.95, threads=4)
+        assert s.cpu().numpy().tobytes() == want.tobytes()
+        assert torch.equal(ZipNN(input_format="torch").decompress(s).cpu().view(torch.int16), t.view(torch.int16))
+        b = torch.randint(0, 256, (kib * 1024,), generator=g, dtype=torch.uint8).numpy().tobytes()
+        zb = ZipNN(input_format="byte", bytearray_dtype="bfloat16")
+        sb = zb.compress(b)
+        assert bytes(ZipNN(input_format="byte", bytearray_dtype="bfloat16").decompress(bytes(sb))) == b
+
+
+def test_streaming_and_delta_frames():
+    g = torch.Generator().manual_seed(2)
+    a = torch.randint(0, 256, (3 * 1024 * 1024 + 17,), generator=g, dtype=torch.uint8).numpy().tobytes()
+    base = (torch.randn(len(a) // 2 + 1, generator=g) * 0.02).to(torch.bfloat16).view(torch.uint8).numpy().tobytes()[: len(a)]
+    for sc in (1 << 19, 1 << 20):
+        z = ZipNN(input_format="byte", bytearray_dtype="bfloat16", is_streaming=True, streaming_chunk=sc)
+        s = z.compress(base)
+        assert bytes(ZipNN(input_format="byte", bytearray_dtype="bfloat16", is_streaming=True, streaming_chunk=sc).decompress(bytes(s))) == base
+        # each frame is an independent reference stream
+        plan = ZipNN(input_format="byte", bytearray_dtype="bfloat16", is_streaming=True, streaming_chunk=sc).plan(base[:sc])
+        first = O.zipnn_compress(plan["header"], np.frombuffer(base[:sc], dtype=np.uint8), 2, 1, 10, 262144, 0.95)
+        assert bytes(s[: first.size]) == first.tobytes()
+    zd = ZipNN(input_format="byte", bytearray_dtype="bfloat16", delta_compressed_type="byte")
+    s = zd.compress(base, delta_second_data=a)
+    out = ZipNN(input_format="byte", bytearray_dtype="bfloat16", delta_compressed_type="byte").decompress(bytes(s), delta_second_data=a)
+    assert bytes(out) == base
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_large_round_trip_properties():
+    """256 MiB bf16: round trip is exact, the stream is deterministic, the chunk table is
+    consistent with the stream length, and the ratio matches the reference's (0.6623)."""
+    n = 128 * 1024 * 1024
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    t = (torch.randn(n, generator=g, device="cuda") * 0.02).to(torch.bfloat16)
+    z = ZipNN(input_format="torch")
+    s1 = z.compress(t)
+    s2 = ZipNN(input_format="torch").compress(t)
+    assert torch.equal(s1, s2)
+    ratio = s1.numel() / (2 * n)
+    assert 0.655 < ratio < 0.670, ratio
+    head = s1[:64].cpu().numpy()
+    assert int.from_bytes(head[24:32].tobytes(), "little") == s1.numel()
+    K = (2 * n + 262143) // 262144
+    hdr_len = 32 + 1 + 5
+    cum = s1[hdr_len + 2 * K: hdr_len + 2 * K + 16 * K].cpu().numpy().view(np.uint64).reshape(2, K)
+    assert hdr_len + 18 * K + int(cum[0, -1]) + int(cum[1, -1]) == s1.numel()
+    assert np.all(np.diff(cum[0].astype(np.int64)) == 131072)  # sign|mantissa plane is stored raw
+    back = ZipNN(input_format="torch").decompress(s1)
+    assert torch.equal(back.view(torch.int16), t.view(torch.int16))
+    # spot-check one window of chunks against the oracle
+    c0 = 301
+    part = t[c0 * 131072: (c0 + 3) * 131072].cpu()
+    plan = ZipNN(input_format="torch").plan(part)
+    want = O.zipnn_compress(plan["header"], np.frombuffer(raw_bytes(part), dtype=np.uint8), 2, 1, 10, 262144, 0.95, threads=3)
+    wcum = want[len(plan["header"]) + 6: len(plan["header"]) + 6 + 48].view(np.uint64).reshape(2, 3)
+    assert int(wcum[1, -1]) == int(cum[1, c0 + 2] - cum[1, c0 - 1])

@@ -1,0 +1,555 @@
+// encode.cuh -- compress side.
+//
+//   pass A  k_encode_stats : per chunk, per byte-group: four per-stream 256-bin histograms,
+//                            then (one warp per group) the reference's block decisions --
+//                            RLE / "not compressible" early-outs, length-limited Huffman
+//                            code lengths, table description, exact compressed size,
+//                            threshold -> type byte + payload size + saved code lengths.
+//   scan    k_encode_scan  : per group inclusive prefix sums of payload sizes -> the
+//                            stream's cumulative table, group bases, item offsets, total
+//                            length, python header.
+//   pass B  k_encode_write : per (chunk, group): raw planes copied, Huffman blocks
+//                            bit-packed (per-thread runs, block-wide exclusive scan of bit
+//                            lengths, OR into a shared bit buffer, word-coalesced flush)
+//                            straight to their final position in the stream.
+//
+// Replaces reference csrc/zipnn_core.c:294-390 (compression_worker), :105-244
+// (prepare_python_return_buffer), hist.c, huf_compress.c:215-724, and the split halves of
+// data_manipulation_dtype16.c:64-138 / data_manipulation_dtype32.c:78-133.
+#pragma once
+#include "common.cuh"
+#include "stage1.cuh"
+
+namespace zb {
+
+// Saved per item by pass A for pass B.
+struct EncSave {
+  uint8_t nb[256];      // code length per symbol (0 = absent)
+  uint8_t hdr[128];     // table description (RLE: hdr[0] = the byte)
+  uint32_t hsize;       // table description bytes
+  uint32_t sbytes[4];   // byte size of each of the 4 bitstreams
+  uint32_t lg;          // table log
+  uint32_t pad[2];
+};
+static_assert(sizeof(EncSave) == 416, "EncSave layout");
+
+constexpr int kEncThreads = 256;
+
+// A byte of the (rotated) chunk at byte position pos; words [0, rot_words) are rotated.
+template <int G>
+__device__ __forceinline__ uint32_t rot_byte_at(const uint8_t* __restrict__ in_c, uint32_t chunk_len, uint32_t rot_words,
+                                                uint32_t pos) {
+  const uint32_t wi = pos >> 2;
+  if (wi >= rot_words) return in_c[pos];
+  (void)chunk_len;
+  const uint32_t w = rot_word<G>(__ldg(reinterpret_cast<const uint32_t*>(in_c) + wi));
+  return (w >> (8 * (pos & 3))) & 0xFFu;
+}
+
+// =====================================================================================
+// pass A
+// =====================================================================================
+template <int G>
+struct StatsSmem {
+  uint32_t rep[G][8][128];   // 8 lane-keyed replicas, two 16-bit counters per word
+  uint16_t hist[G][4][256];  // per stream
+  uint32_t total[G][256];
+  uint8_t nb[G][256];
+  uint8_t nzsym[G][256];
+  TreeScratch tree[G];
+};
+
+template <int G>
+__device__ __forceinline__ void hist_add(StatsSmem<G>& S, int g, int r, uint32_t b) {
+  atomicAdd(&S.rep[g][r][b >> 1], 1u << (16 * (b & 1)));
+}
+
+// One warp: everything the reference does per block after the histogram
+// (huf_compress.c:671-724 + csrc/zipnn_core.c:371-385).
+template <int G>
+__device__ void warp_block_decision(StatsSmem<G>& S, int g, uint32_t plen, uint32_t chunk_cap, double thr,
+                                    uint8_t* type_out, uint32_t* size_out, EncSave* save) {
+  const int lane = threadIdx.x & 31;
+  uint32_t* total = S.total[g];
+  uint32_t largest = 0;
+  int max_sym = -1;
+  for (int s = lane; s < 256; s += 32) {
+    const uint32_t t = (uint32_t)S.hist[g][0][s] + S.hist[g][1][s] + S.hist[g][2][s] + S.hist[g][3][s];
+    total[s] = t;
+    largest = max(largest, t);
+    if (t) max_sym = s;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    largest = max(largest, __shfl_xor_sync(0xffffffffu, largest, o));
+    max_sym = max(max_sym, __shfl_xor_sync(0xffffffffu, max_sym, o));
+  }
+  __syncwarp();
+  uint8_t type = 0;
+  uint32_t size = plen;
+  bool huf = false;
+  if (plen == 0 || plen > (uint32_t)kHufBlockMax) {
+    // empty plane, or HUF_compress rejects > 128 KiB (huf_compress.c:658) -> raw
+  } else if (largest == plen) {
+    if (1.0 < (double)plen * thr) {  // RLE block of 1 byte (huf_compress.c:673)
+      type = 1;
+      size = 1;
+      if (lane == 0) {
+        save->hdr[0] = (uint8_t)max_sym;
+        save->hsize = 0;
+      }
+    }
+  } else if (largest <= (plen >> 7) + 4) {
+    // heuristic "probably not compressible" (huf_compress.c:674)
+  } else {
+    huf = true;
+  }
+  if (huf) {
+    // ---- order the present symbols: count descending, symbol ascending ----
+    TreeScratch& T = S.tree[g];
+    uint8_t* nz = S.nzsym[g];
+    int k = 0;
+    for (int base = 0; base < 256; base += 32) {
+      const int s = base + lane;
+      const bool p = total[s] != 0;
+      const uint32_t m = __ballot_sync(0xffffffffu, p);
+      if (p) nz[k + __popc(m & ((1u << lane) - 1u))] = (uint8_t)s;
+      k += __popc(m);
+    }
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+      const uint32_t c = total[nz[i]];
+      int rank = 0;
+      for (int j = 0; j < k; j++) {
+        const uint32_t cj = total[nz[j]];
+        rank += (cj > c) || (cj == c && j < i);
+      }
+      T.cnt[rank] = c;
+      T.sym[rank] = nz[i];
+    }
+    __syncwarp();
+    int lg = 0, hsize = -1;
+    if (lane == 0) {
+      const int want = fse_pick_log(kHufLogDefault, plen, (uint32_t)max_sym, 1);
+      lg = huf_lengths_from_sorted(T, k - 1, want, S.nb[g]);
+      hsize = huf_write_table(T, S.nb[g], max_sym, lg);
+    }
+    lg = __shfl_sync(0xffffffffu, lg, 0);
+    hsize = __shfl_sync(0xffffffffu, hsize, 0);
+    __syncwarp();
+    if (hsize > 0 && (uint32_t)hsize + 12 < plen && plen >= 12) {
+      uint32_t bits[4] = {0, 0, 0, 0};
+      for (int s = lane; s <= max_sym; s += 32) {
+        const uint32_t l = S.nb[g][s];
+#pragma unroll
+        for (int q = 0; q < 4; q++) bits[q] += (uint32_t)S.hist[g][q][s] * l;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bits[q] += __shfl_xor_sync(0xffffffffu, bits[q], o);
+      uint32_t sb[4], csize = (uint32_t)hsize + 6;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        sb[q] = (bits[q] >> 3) + 1;  // ceil((bits + end mark) / 8), bitstream.h:254-260
+        csize += sb[q];
+      }
+      (void)chunk_cap;  // dst capacity (= chunk) can only bind when the block is kept raw anyway
+      if (csize < plen - 1 && (double)csize < (double)plen * thr) {  // huf_compress.c:625, zipnn_core.c:371-373
+        type = 1;
+        size = csize;
+        for (int s = lane; s < 256; s += 32) save->nb[s] = S.nb[g][s];
+        for (int i = lane; i < hsize; i += 32) save->hdr[i] = T.hdr[i];
+        if (lane == 0) {
+          save->hsize = (uint32_t)hsize;
+          save->lg = (uint32_t)lg;
+#pragma unroll
+          for (int q = 0; q < 4; q++) save->sbytes[q] = sb[q];
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    *type_out = type;
+    *size_out = size;
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kEncThreads) k_encode_stats(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk,
+                                                              uint64_t K, int bits_mode, double thr, uint8_t* types,
+                                                              uint32_t* sizes, EncSave* saves) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StatsSmem<G>& S = *reinterpret_cast<StatsSmem<G>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, rep = lane & 7;
+  for (uint64_t c = blockIdx.x; c < K; c += gridDim.x) {
+    const uint8_t* in_c = in + c * (uint64_t)chunk;
+    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
+    const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;
+    const bool fast = (chunk_len % 64u) == 0;
+    for (int q = 0; q < 4; q++) {
+      for (int i = tid; i < G * 8 * 128; i += kEncThreads) (&S.rep[0][0][0])[i] = 0;
+      __syncthreads();
+      if (fast) {
+        const uint32_t qbytes = chunk_len >> 2;  // bytes of input per stream quarter
+        const uint4* src = reinterpret_cast<const uint4*>(in_c + (uint64_t)q * qbytes);
+        for (uint32_t u = tid; u < (qbytes >> 4); u += kEncThreads) {
+          const uint4 v = __ldg(src + u);
+          uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            if (rot_words) w[i] = rot_word<G>(w[i]);
+#pragma unroll
+            for (int b = 0; b < 4; b++) hist_add<G>(S, (4 * i + b) % G, rep, (w[i] >> (8 * b)) & 0xFFu);
+          }
+        }
+      } else {
+        for (int g = 0; g < G; g++) {
+          const uint32_t pl = plane_len(chunk_len, G, g);
+          const uint32_t seg = (pl + 3) >> 2;
+          const uint32_t j0 = min(pl, (uint32_t)q * seg), j1 = (q == 3) ? pl : min(pl, j0 + seg);
+          for (uint32_t j = j0 + tid; j < j1; j += kEncThreads)
+            hist_add<G>(S, g, rep, rot_byte_at<G>(in_c, chunk_len, rot_words, j * G + g));
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < G * 256; i += kEncThreads) {
+        const int g = i >> 8, b = i & 255;
+        uint32_t t = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t += (S.rep[g][r][b >> 1] >> (16 * (b & 1))) & 0xFFFFu;
+        S.hist[g][q][b] = (uint16_t)t;
+      }
+      __syncthreads();
+    }
+    const int warp = tid >> 5;
+    if (warp < G) {
+      const uint64_t item = (uint64_t)warp * K + c;
+      warp_block_decision<G>(S, warp, plane_len(chunk_len, G, warp), chunk, thr, types + item, sizes + item, saves + item);
+    }
+    __syncthreads();
+  }
+}
+
+// =====================================================================================
+// scan: sizes -> cumulative table (written into the stream), bases, item offsets, header.
+// =====================================================================================
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads) k_encode_scan(const uint32_t* __restrict__ sizes, const uint8_t* __restrict__ types,
+                                                              int G, uint64_t K, const uint8_t* __restrict__ hdr_dev,
+                                                              uint32_t hdr_len, uint8_t* out, uint64_t* item_off, Ctrl* ctrl) {
+  __shared__ uint64_t warp_tot[32];
+  __shared__ uint64_t carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t nitems = (uint64_t)G * K;
+  uint8_t* cum_out = out + hdr_len + nitems;
+  const uint64_t payload0 = (uint64_t)hdr_len + 9 * nitems;
+  uint64_t base = payload0;
+  for (uint64_t i = tid; i < nitems; i += kScanThreads) out[hdr_len + i] = types[i];
+  for (int g = 0; g < G; g++) {
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t c0 = 0; c0 < K; c0 += kScanThreads) {
+      const uint64_t c = c0 + tid;
+      const uint64_t v = (c < K) ? sizes[(uint64_t)g * K + c] : 0;
+      uint64_t x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) warp_tot[warp] = x;
+      __syncthreads();
+      uint64_t pre = carry_s;
+      for (int w = 0; w < warp; w++) pre += warp_tot[w];
+      const uint64_t incl = pre + x;
+      if (c < K) {
+        st_u64_bytes(cum_out + 8 * ((uint64_t)g * K + c), incl);
+        item_off[(uint64_t)g * K + c] = base + incl - v;
+      }
+      __syncthreads();
+      if (tid == kScanThreads - 1) carry_s = incl;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      ctrl->base[g] = base;
+      ctrl->group_total[g] = carry_s;
+    }
+    base += carry_s;
+    __syncthreads();
+  }
+  // python header with the total length patched in (csrc/zipnn_core.c:121)
+  for (uint32_t i = tid; i < hdr_len; i += kScanThreads) {
+    uint8_t b = hdr_dev[i];
+    if (i >= 24 && i < 32) b = (uint8_t)(base >> (8 * (i - 24)));
+    out[i] = b;
+  }
+  if (tid == 0) ctrl->total_len = base;
+}
+
+// =====================================================================================
+// pass B
+// =====================================================================================
+constexpr uint32_t kEncTile = kEncThreads * 16;             // plane bytes per tile (4096)
+constexpr uint32_t kBitBufWords = (kEncTile * 11) / 32 + 8;  // worst-case tile bits + carry
+
+struct WriteSmem {
+  __align__(16) uint8_t tile[kEncTile + 16];
+  uint32_t bitbuf[kBitBufWords];
+  uint32_t code[256];  // val | nb << 16
+  uint32_t warp_sum[kEncThreads / 32];
+  EncSave save;
+};
+
+// Fill S.tile[0..cnt) with bytes [p0, p0+cnt) of plane g of the (rotated) chunk.
+template <int G>
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restrict__ in_c, uint32_t chunk_len,
+                                           uint32_t rot_words, int g, uint32_t p0, uint32_t cnt) {
+  const int tid = threadIdx.x;
+  const bool fast = ((p0 * G) % 16u) == 0 && (cnt % 16u) == 0 && ((p0 + cnt) * (uint32_t)G <= (chunk_len & ~3u));
+  if (fast) {
+    for (uint32_t u = tid; u < (cnt >> 4); u += kEncThreads) {
+      const uint4* src = reinterpret_cast<const uint4*>(in_c + (uint64_t)(p0 + 16 * u) * G);
+      uint32_t w[4 * G];
+#pragma unroll
+      for (int i = 0; i < G; i++) {
+        const uint4 v = __ldg(src + i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+      }
+      if (rot_words) {
+#pragma unroll
+        for (int i = 0; i < 4 * G; i++) w[i] = rot_word<G>(w[i]);
+      }
+      uint4 pv[G];
+      split16<G>(w, pv);
+      uint4 mine = pv[0];
+#pragma unroll
+      for (int k = 1; k < G; k++)
+        if (g == k) mine = pv[k];
+      *reinterpret_cast<uint4*>(tile + 16 * u) = mine;
+    }
+  } else {
+    for (uint32_t j = tid; j < cnt; j += kEncThreads)
+      tile[j] = (uint8_t)rot_byte_at<G>(in_c, chunk_len, rot_words, (p0 + j) * G + g);
+  }
+}
+
+// Copy tile[0..cnt) to the (arbitrarily aligned) global address dst.
+__device__ __forceinline__ void tile_to_global(const uint8_t* tile, uint8_t* dst, uint32_t cnt) {
+  const int tid = threadIdx.x;
+  const uint32_t head = min(cnt, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
+  if ((uint32_t)tid < head) dst[tid] = tile[tid];
+  const uint32_t nvec = (cnt - head) >> 4;
+  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(tile);
+  for (uint32_t v = tid; v < nvec; v += kEncThreads) {
+    const uint32_t o = head + 16 * v;
+    const uint32_t sh = (o & 3) * 8;
+    const uint32_t* p = t32 + (o >> 2);
+    const uint32_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4];  // tile has 16 B of slack
+    *reinterpret_cast<uint4*>(dst + o) = make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh),
+                                                    __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh));
+  }
+  const uint32_t done = head + 16 * nvec;
+  if ((uint32_t)tid < cnt - done) dst[done + tid] = tile[done + tid];
+}
+
+// Canonical code values from lengths, one warp (huf_compress.c:390-407).
+__device__ __forceinline__ void warp_build_codes(const uint8_t* nb, int lg, uint32_t* code) {
+  const int lane = threadIdx.x & 31;
+  uint32_t per_len[kHufLogMax + 1];
+#pragma unroll
+  for (int l = 0; l <= kHufLogMax; l++) per_len[l] = 0;
+  for (int base = 0; base < 256; base += 32) {
+    const int mine = nb[base + lane];
+#pragma unroll
+    for (int l = 1; l <= kHufLogMax; l++) per_len[l] += __popc(__ballot_sync(0xffffffffu, mine == l));
+  }
+  uint32_t start[kHufLogMax + 1];
+  {
+    uint32_t v = 0;
+#pragma unroll
+    for (int l = kHufLogMax; l >= 1; l--) {
+      if (l <= lg) {
+        start[l] = v;
+        v = (v + per_len[l]) >> 1;
+      } else {
+        start[l] = 0;
+      }
+    }
+  }
+  for (int base = 0; base < 256; base += 32) {
+    const int mine = nb[base + lane];
+    uint32_t val = 0;
+#pragma unroll
+    for (int l = 1; l <= kHufLogMax; l++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, mine == l);
+      if (mine == l) val = start[l] + __popc(m & ((1u << lane) - 1u));
+      start[l] += __popc(m);
+    }
+    code[base + lane] = val | ((uint32_t)mine << 16);
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kEncThreads) k_encode_write(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk, uint64_t K,
+                                                              int bits_mode, const uint8_t* __restrict__ types,
+                                                              const uint32_t* __restrict__ sizes, const EncSave* __restrict__ saves,
+                                                              const uint64_t* __restrict__ item_off, uint8_t* out) {
+  __shared__ WriteSmem S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t nitems = (uint64_t)G * K;
+  for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int g = (int)(item / K);
+    const uint64_t c = item - (uint64_t)g * K;
+    const uint8_t* in_c = in + c * (uint64_t)chunk;
+    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
+    const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;
+    const uint32_t plen = plane_len(chunk_len, G, g);
+    uint8_t* dest = out + item_off[item];
+    const uint8_t type = types[item];
+    const uint32_t size = sizes[item];
+    if (plen == 0) continue;
+    __syncthreads();
+    if (type == 0) {
+      for (uint32_t p0 = 0; p0 < plen; p0 += kEncTile) {
+        const uint32_t cnt = min(kEncTile, plen - p0);
+        stage_tile<G>(S.tile, in_c, chunk_len, rot_words, g, p0, cnt);
+        __syncthreads();
+        tile_to_global(S.tile, dest + p0, cnt);
+        __syncthreads();
+      }
+      continue;
+    }
+    if (size == 1) {
+      if (tid == 0) dest[0] = saves[item].hdr[0];
+      continue;
+    }
+    // ---- Huffman block: table description, jump table, 4 bitstreams ----
+    {
+      const uint32_t* sv = reinterpret_cast<const uint32_t*>(saves + item);
+      uint32_t* dv = reinterpret_cast<uint32_t*>(&S.save);
+      for (int i = tid; i < (int)(sizeof(EncSave) / 4); i += kEncThreads) dv[i] = sv[i];
+    }
+    __syncthreads();
+    const uint32_t hsize = S.save.hsize;
+    if (warp == 0) warp_build_codes(S.save.nb, (int)S.save.lg, S.code);
+    if (warp == 1) {
+      for (uint32_t i = lane; i < hsize; i += 32) dest[i] = S.save.hdr[i];
+      if (lane < 3) {
+        dest[hsize + 2 * lane] = (uint8_t)S.save.sbytes[lane];
+        dest[hsize + 2 * lane + 1] = (uint8_t)(S.save.sbytes[lane] >> 8);
+      }
+    }
+    __syncthreads();
+    const uint32_t seg = (plen + 3) >> 2;
+    uint32_t stream_at = hsize + 6;
+    for (int i = 0; i < 4; i++) {
+      const uint32_t s_begin = (uint32_t)i * seg;
+      const uint32_t s_end = (i == 3) ? plen : s_begin + seg;
+      uint8_t* gaddr = dest + stream_at;
+      const uint32_t sbytes = S.save.sbytes[i];
+      stream_at += sbytes;
+      const uint32_t a = (uint32_t)((uintptr_t)gaddr & 3);
+      uint32_t* gword = reinterpret_cast<uint32_t*>(gaddr - a);
+      uint32_t B = 8 * a;       // bits placed so far, counted from the aligned word base
+      uint32_t flushed = 0;     // whole words already written to global
+      for (uint32_t w = tid; w < kBitBufWords; w += kEncThreads) S.bitbuf[w] = 0;
+      __syncthreads();
+      for (uint32_t p1 = s_end; p1 > s_begin;) {
+        const uint32_t p0 = (p1 - s_begin > kEncTile) ? p1 - kEncTile : s_begin;
+        const uint32_t cnt = p1 - p0;
+        stage_tile<G>(S.tile, in_c, chunk_len, rot_words, g, p0, cnt);
+        __syncthreads();
+        // ---- this thread's 16 symbols, in emission order (last plane byte first) ----
+        const uint32_t e0 = 16u * tid;
+        const int nvalid = (int)min(16u, cnt > e0 ? cnt - e0 : 0u);
+        uint64_t v[4] = {0, 0, 0, 0};
+        uint32_t l[4] = {0, 0, 0, 0};
+        if (nvalid == 16 && (cnt & 15u) == 0) {
+          const uint4 q = *reinterpret_cast<const uint4*>(S.tile + (cnt - 16 - e0));
+          const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const uint32_t sym = (wv[(15 - k) >> 2] >> (8 * ((15 - k) & 3))) & 0xFFu;
+            const uint32_t cd = S.code[sym];
+            v[k >> 2] |= (uint64_t)(cd & 0xFFFFu) << l[k >> 2];
+            l[k >> 2] += cd >> 16;
+          }
+        } else {
+          for (int k = 0; k < nvalid; k++) {
+            const uint32_t cd = S.code[S.tile[cnt - 1 - (e0 + k)]];
+            v[k >> 2] |= (uint64_t)(cd & 0xFFFFu) << l[k >> 2];
+            l[k >> 2] += cd >> 16;
+          }
+        }
+        const uint32_t mine = l[0] + l[1] + l[2] + l[3];
+        // ---- block-wide exclusive scan of bit lengths ----
+        uint32_t x = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += y;
+        }
+        if (lane == 31) S.warp_sum[warp] = x;
+        __syncthreads();
+        uint32_t pre = 0, tile_bits = 0;
+#pragma unroll
+        for (int w = 0; w < kEncThreads / 32; w++) {
+          const uint32_t t = S.warp_sum[w];
+          if (w < warp) pre += t;
+          tile_bits += t;
+        }
+        uint32_t off = (B - 32 * flushed) + pre + x - mine;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (l[r]) {
+            const uint32_t sh = off & 31, wi = off >> 5;
+            const uint32_t lo32 = (uint32_t)v[r], hi32 = (uint32_t)(v[r] >> 32);
+            const uint32_t w0 = lo32 << sh;
+            const uint32_t w1 = __funnelshift_l(lo32, hi32, sh);
+            const uint32_t w2 = sh ? (hi32 >> (32 - sh)) : 0u;
+            if (w0) atomicOr(&S.bitbuf[wi], w0);
+            if (w1) atomicOr(&S.bitbuf[wi + 1], w1);
+            if (w2) atomicOr(&S.bitbuf[wi + 2], w2);
+            off += l[r];
+          }
+        }
+        __syncthreads();
+        B += tile_bits;
+        // ---- flush the words that are complete ----
+        const uint32_t complete = (B >> 5) - flushed;
+        for (uint32_t w = tid; w < complete; w += kEncThreads) {
+          const uint32_t val = S.bitbuf[w];
+          if (flushed + w == 0 && a != 0) {
+            for (uint32_t bb = a; bb < 4; bb++) gaddr[bb - a] = (uint8_t)(val >> (8 * bb));
+          } else {
+            gword[flushed + w] = val;
+          }
+        }
+        const uint32_t carry = S.bitbuf[complete];
+        __syncthreads();
+        for (uint32_t w = tid; w <= complete + 1 && w < kBitBufWords; w += kEncThreads) S.bitbuf[w] = 0;
+        __syncthreads();
+        if (tid == 0) S.bitbuf[0] = carry;
+        flushed += complete;
+        p1 = p0;
+        __syncthreads();
+      }
+      // ---- end mark + the last (partial) bytes ----
+      if (tid == 0) S.bitbuf[(B - 32 * flushed) >> 5] |= 1u << (B & 31);
+      __syncthreads();
+      {
+        const uint32_t first_byte = max(4 * flushed, a);   // relative to the aligned base
+        const uint32_t end_byte = a + sbytes;              // exclusive
+        for (uint32_t bb = first_byte + tid; bb < end_byte; bb += kEncThreads) {
+          const uint32_t rel = bb - 4 * flushed;
+          gaddr[bb - a] = (uint8_t)(S.bitbuf[rel >> 2] >> (8 * (rel & 3)));
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace zb

@@ -1,0 +1,461 @@
+"""`ZipNN` -- host-side mirror of the reference codec object, routed to the B200 kernels.
+
+Same constructor, same `compress()` / `decompress()` contract and the same stream bytes as
+reference `zipnn/zipnn.py:27-1218`; the native calls `zipnn_core.zipnn_core(...)`
+(`zipnn/zipnn.py:714-725`) and `zipnn_core.combine_dtype(...)` (`:1143-1151`) are replaced by
+the C ABI in `include/zipnn_b200.h`.
+
+What is new relative to the reference:
+  * a CUDA tensor in gives a CUDA tensor out (the compressed stream as `uint8`, or the
+    decoded tensor), with no host round trip;
+  * host inputs (CPU tensors, bytes, numpy) still work -- they are copied to the GPU, coded
+    there and copied back (there is NO CPU codec in this package);
+  * the input is never modified (the reference rotates sign bits in place).
+
+Not carried over (out of the hot path): zstd/lz4/snappy methods, lossy
+modes (dead code in the reference), the uint32/numpy truncation paths (they raise in the
+reference as well), file-path arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import multiprocessing
+
+import numpy as np
+import torch
+
+from . import _native
+from .util_header import EnumFormat, EnumLossy, EnumMethod
+from .util_torch import (
+    BFLOAT16, FLOAT, FLOAT16, FLOAT32, FLOAT8_E4M3FN, FLOAT8_E5M2, HALF, UINT32,
+    dtype_code, torch_dtype_of_code, zipnn_is_floating_point, zipnn_pack_shape, zipnn_unpack_shape,
+)
+
+HEADER_LEN = 32
+HUF_MAX_BLOCK = 128 * 1024  # fp8 planes are whole chunks, and a Huffman block holds at most 128 KiB
+
+
+def _as_u8_numpy(data) -> np.ndarray:
+    """Zero-copy uint8 view of a bytes-like object / numpy array."""
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data).reshape(-1).view(np.uint8)
+    return np.frombuffer(data, dtype=np.uint8)
+
+
+def _layout_for_dtype(code: int):
+    """(bit_reorder, byte_reorder, num_buf) per dtype: reference zipnn/zipnn.py:788-815."""
+    if code in (FLOAT8_E4M3FN, FLOAT8_E5M2):
+        return 1, 10, 1          # bit_reorder is recorded but ignored by the fp8 path
+    if code in (FLOAT32, FLOAT):
+        return 1, 220, 4
+    if code == BFLOAT16:
+        return 1, 10, 2
+    if code in (FLOAT16, HALF):
+        return 0, 10, 2
+    raise ValueError("Support only torch.dtype float32/bfloat16/float16")
+
+
+class ZipNN:
+    def __init__(
+        self,
+        method: str = "AUTO",
+        input_format: str = "byte",
+        bytearray_dtype: str = "bfloat16",
+        is_monotonic: int = 0,
+        threads: int = 0,
+        compression_threshold=0.95,
+        check_th_after_percent=10,
+        byte_reorder: int = 0,
+        reorder_signbit: int = 0,
+        delta_compressed_type: str = 0,
+        lossy_compressed_type: str = 0,
+        lossy_compressed_factor=27,
+        compression_chunk=256 * 1024,
+        is_streaming: bool = False,
+        streaming_chunk: int = 1024 * 1024,
+        input_file: str = None,
+        compressed_file: str = None,
+        decompressed_file: str = None,
+        zstd_level: int = 3,
+        lz4_compression_level: int = 0,
+    ):
+        """Same keyword arguments as the reference (zipnn/zipnn.py:29-51).
+
+        `threads`, `check_th_after_percent`, `is_monotonic`, `zstd_level`,
+        `lz4_compression_level` are accepted for compatibility and have no effect on the GPU
+        path (`check_th_after_percent` has none in the reference either,
+        csrc/zipnn_core.c:555-558).
+        """
+        self.method = EnumMethod(method).value
+        self.input_format = EnumFormat(input_format).value
+        self.bytearray_dtype = bytearray_dtype
+        self.is_monotonic = is_monotonic
+        self.threads = threads or min(multiprocessing.cpu_count(), 16)
+        self.compression_threshold = compression_threshold
+        self.check_th_after_percent = check_th_after_percent
+        self.byte_reorder = byte_reorder
+        self.reorder_signbit = reorder_signbit
+        self.delta_compressed_type = delta_compressed_type
+        self.lossy_compressed_type = EnumLossy.NONE if lossy_compressed_type is None else EnumLossy(lossy_compressed_type)
+        self.lossy_compressed_factor = lossy_compressed_factor
+
+        if compression_chunk > 0 and (compression_chunk & (compression_chunk - 1)) == 0:
+            self.compression_chunk = compression_chunk
+        else:
+            raise ValueError("compression_chunk must be a number that is a power of 2.")
+        if self.input_format != EnumFormat.BYTE.value and is_streaming:
+            raise ValueError("Streaming is currently implemented only for bytes data type.")
+        self.is_streaming = is_streaming
+        if streaming_chunk > 0 and (streaming_chunk & (streaming_chunk - 1)) == 0:
+            self.streaming_chunk = streaming_chunk
+        else:
+            raise ValueError("streaming_chunk must be a number that is a power of 2.")
+
+        self.input_file = input_file
+        self.compressed_file = compressed_file
+        self.decompressed_file = decompressed_file
+        self.lz4_compression_level = lz4_compression_level
+
+        self._version_major, self._version_minor, self._version_tiny = 0, 5, 3
+        if self.method not in (EnumMethod.AUTO.value, EnumMethod.HUFFMAN.value):
+            # reference: these need the optional zstandard / lz4 / snappy wheels and are only
+            # reachable for one-group byte_reorder modes that no float dtype selects
+            raise ImportError(f"method {EnumMethod(self.method).name} is not part of the B200 path; use AUTO or HUFFMAN")
+        if self.lossy_compressed_type != EnumLossy.NONE and self.input_format != EnumFormat.TORCH.value:
+            raise ValueError("When use lossy compression the input have to be torch.tensor")
+
+        self.header_length = HEADER_LEN
+        self._header = bytearray(self.header_length)
+        self._ext_header = b""
+        self._shape_size = 0
+        self._update_header()
+
+    # ------------------------------------------------------------------ header
+    # [0:2]="ZN" [2:5]=version [5]=byte_reorder [6]=bit_reorder [7]=method [8]=format [9]=delta
+    # [10:13]=lossy [13]=streaming [14]=log2(chunk) [15]=dtype [16:24]=orig len [24:32]=stream len
+    # (zipnn/zipnn.py:287-303, 355-394)
+    def _update_header(self):
+        h = self._header
+        h[0:2] = b"ZN"
+        h[2], h[3], h[4] = self._version_major, self._version_minor, self._version_tiny
+        h[7] = self.method
+        h[8] = self.input_format
+        h[9] = 1 if self.delta_compressed_type == "byte" else 2 if self.delta_compressed_type == "file" else 0
+        h[13] = 128 + int(math.log(self.streaming_chunk, 2)) if self.is_streaming else 0
+        h[14] = int(math.log(self.compression_chunk, 2))
+
+    def _retrieve_header(self, head: bytes) -> int:
+        """Parse the 32-byte header (+ packed shape); returns where the body starts
+        (zipnn/zipnn.py:396-438)."""
+        header = head[: self.header_length]
+        if len(header) < self.header_length or header[0:2] != b"ZN":
+            raise ValueError("Header should start with ZN")
+        self.version_major, self.version_minor, self.version_tiny = header[2], header[3], header[4]
+        self._byte_reorder = header[5]
+        self._bit_reorder = header[6]
+        self.method = header[7]
+        self.input_format = header[8]
+        self.lossy_compressed_type = header[10]
+        self.lossy_compressed_factor = header[11]
+        self._lossy_is_int = header[12]
+        self.is_streaming = 1 if header[13] > 127 else 0
+        self.compression_chunk = 2 ** header[14]
+        self.dtype = header[15]
+        self.original_len = int.from_bytes(header[16:24], "little")
+        self._shape_size = 0
+        if self.input_format in (EnumFormat.TORCH.value, EnumFormat.NUMPY.value):
+            self.shape_bytes, self._shape_size = zipnn_unpack_shape(head[self.header_length:])
+        return self.header_length + self._shape_size
+
+    # ------------------------------------------------------------------ compress
+    def compress(self, data, compress_cpu_gpu="cpu", delta_second_data=None, lossy_compressed_type: str = None,
+                 lossy_compressed_factor: int = None):
+        """zipnn/zipnn.py:560-643.  Returns a `memoryview` for host inputs (as the reference
+        does) or a CUDA `uint8` tensor for CUDA inputs (or when compress_cpu_gpu == "gpu")."""
+        self._want_device_result = (compress_cpu_gpu == "gpu")
+        if self.delta_compressed_type == "byte":
+            if len(data) != len(delta_second_data):
+                raise ValueError("Length of delta file has to match the length of the original file.")
+        elif self.delta_compressed_type == "file":
+            try:
+                with open(delta_second_data, "rb") as file:
+                    delta_second_data = file.read()
+            except Exception:
+                raise FileNotFoundError("Encountered an error when reading the delta file")
+            if len(data) != len(delta_second_data):
+                raise ValueError("Length of delta file has to match the length of the original file.")
+        elif delta_second_data is not None:
+            raise ValueError("ZipNN isn't set for delta compression, but delta_second_data is not null.")
+
+        if self.is_streaming and self.input_format == EnumFormat.BYTE.value:
+            # independent frames of `streaming_chunk` input bytes (zipnn/zipnn.py:612-635)
+            src = _as_u8_numpy(data)
+            dlt = _as_u8_numpy(delta_second_data) if delta_second_data is not None else None
+            out = bytearray()
+            for off in range(0, src.size, self.streaming_chunk):
+                piece = src[off: off + self.streaming_chunk]
+                if dlt is not None:
+                    piece = np.bitwise_xor(piece, dlt[off: off + self.streaming_chunk])
+                out.extend(self.compress_torch_numpy_byte(piece))
+            return out
+        if delta_second_data is not None:
+            data = np.bitwise_xor(_as_u8_numpy(data), _as_u8_numpy(delta_second_data))
+        return self.compress_torch_numpy_byte(data)
+
+    def compress_torch_numpy_byte(self, data, lossy_compressed_type=None, lossy_compressed_factor=None):
+        """dtype dispatch + byte view of the input: zipnn/zipnn.py:748-867."""
+        fmt = self.input_format
+        if fmt == EnumFormat.BYTE.value:
+            code = dtype_code(self.bytearray_dtype)
+            shape = None
+        else:
+            code = dtype_code(data.dtype)
+            shape = tuple(data.shape)
+        if not zipnn_is_floating_point(fmt, data, self.bytearray_dtype):
+            if code == UINT32 and fmt == EnumFormat.NUMPY.value:
+                raise ValueError("Not support uint32 with NumPy format")
+            raise ValueError("Support only uint32 with NumPy format")
+        bit_reorder, byte_reorder, num_buf = _layout_for_dtype(code)
+        self._header[5], self._header[6], self._header[15] = byte_reorder, bit_reorder, code
+
+        if fmt == EnumFormat.TORCH.value:
+            t = data.detach().contiguous().reshape(-1)
+            flat = t.view(torch.uint8) if t.dtype != torch.uint8 else t
+        elif fmt == EnumFormat.NUMPY.value:
+            flat = torch.from_numpy(np.ascontiguousarray(data).reshape(-1).view(np.uint8))
+        elif isinstance(data, torch.Tensor):   # byte format, bytes held in a (possibly CUDA) uint8 tensor
+            flat = data.detach().contiguous().reshape(-1).view(torch.uint8)
+        else:
+            flat = _as_u8_numpy(data)     # host bytes: stays a numpy view (may be read-only)
+        return self.compress_bin(flat, bit_reorder, byte_reorder, num_buf, shape)
+
+    def _plan_header(self, n: int, num_buf: int, shape):
+        """-> (python_header bytes, chunk) for an input of n bytes (zipnn/zipnn.py:709-721)."""
+        self._header[16:24] = int(n).to_bytes(8, "little")
+        self._ext_header = zipnn_pack_shape(shape) if self.input_format in (EnumFormat.TORCH.value, EnumFormat.NUMPY.value) else b""
+        chunk = self.compression_chunk if num_buf != 1 else min(HUF_MAX_BLOCK, self.compression_chunk)
+        return bytes(self._header) + self._ext_header, chunk
+
+    def compress_bin(self, flat_u8, bit_reorder: int, byte_reorder: int, num_buf: int, shape):
+        """Header assembly + the native call (zipnn/zipnn.py:670-746).  `flat_u8` is a flat uint8
+        view of the input: a torch tensor (CPU or CUDA) or a numpy array (host bytes)."""
+        n = flat_u8.numel() if isinstance(flat_u8, torch.Tensor) else flat_u8.size
+        python_header, chunk = self._plan_header(n, num_buf, shape)
+        self._last_plan = dict(header=python_header, num_buf=num_buf, bit_reorder=bit_reorder,
+                               byte_reorder=byte_reorder, chunk=chunk, threshold=self.compression_threshold)
+        if getattr(self, "_plan_only", False):
+            return None
+        if isinstance(flat_u8, torch.Tensor) and flat_u8.is_cuda:
+            return _compress_device(flat_u8, python_header, num_buf, bit_reorder, byte_reorder, chunk, self.compression_threshold)
+        out = _compress_host(flat_u8, python_header, num_buf, bit_reorder, byte_reorder, chunk, self.compression_threshold)
+        if getattr(self, "_want_device_result", False):
+            return torch.from_numpy(np.asarray(out)).cuda()
+        return out
+
+    def plan(self, data) -> dict:
+        """Everything `compress(data)` would hand to the native call, without calling it:
+        {header, num_buf, bit_reorder, byte_reorder, chunk, threshold}.  Needs no GPU."""
+        self._plan_only = True
+        try:
+            self.compress_torch_numpy_byte(data)
+        finally:
+            self._plan_only = False
+        return self._last_plan
+
+    # ------------------------------------------------------------------ decompress
+    def decompress(self, data, decompress_cpu_gpu="cpu", delta_second_data=None):
+        """zipnn/zipnn.py:928-1005.  CUDA `uint8` tensor in -> CUDA result; host bytes in -> host result."""
+        if self.delta_compressed_type == "byte":
+            if delta_second_data is None:
+                raise ValueError("delta_second_data is None or not set for delta copression")
+        elif self.delta_compressed_type == "file":
+            try:
+                with open(delta_second_data, "rb") as file:
+                    delta_second_data = file.read()
+            except Exception:
+                raise FileNotFoundError("Encountered an error when reading the delta file")
+        elif delta_second_data is not None:
+            raise ValueError("ZipNN isn't set for delta compression, but delta_second_data is not null.")
+
+        stream = _as_stream(data)
+        head = _peek(stream, 64)
+        if len(head) < HEADER_LEN:
+            raise ValueError("Header should start with ZN")
+        was_delta = head[9]
+        if was_delta == 0 and self.delta_compressed_type != 0:
+            raise ValueError("The data wasn't compressed using delta compression and you're trying to delta-decompress it.")
+        if was_delta != 0 and self.delta_compressed_type == 0:
+            raise ValueError("The data was compressed using delta compression and you're trying to decompress it normally.")
+
+        if self.input_format == EnumFormat.BYTE.value and head[13] > 127:
+            # concatenated frames, each [32-byte header][body]; frame length at header[24:32]
+            if isinstance(stream, torch.Tensor):
+                stream = stream.cpu().numpy()
+            dlt = _as_u8_numpy(delta_second_data) if delta_second_data is not None else None
+            out = bytearray()
+            off, doff = 0, 0
+            while off < stream.size:
+                flen = int.from_bytes(stream[off + 24: off + 32].tobytes(), "little")
+                if flen < HEADER_LEN or off + flen > stream.size:
+                    raise RuntimeError("corrupt ZipNN streaming frame")
+                piece = np.frombuffer(self.decompress_bin(stream[off: off + flen]), dtype=np.uint8)
+                if dlt is not None:
+                    if doff + piece.size > dlt.size:
+                        raise ValueError("Length of delta file has to match the length of the decompressed file.")
+                    piece = np.bitwise_xor(piece, dlt[doff: doff + piece.size])
+                    doff += piece.size
+                out.extend(piece.tobytes())
+                off += flen
+            if dlt is not None and doff != dlt.size:
+                raise ValueError("Length of delta file has to match the length of the decompressed file.")
+            return out
+
+        result = self.decompress_bin(stream)
+        if delta_second_data is not None:
+            dec = _as_u8_numpy(result)
+            dlt = _as_u8_numpy(delta_second_data)
+            if dec.size != dlt.size:
+                raise ValueError("Length of delta file has to match the length of the decompressed file.")
+            return np.bitwise_xor(dec, dlt).tobytes()
+        return result
+
+    def decompress_bin(self, stream):
+        """Header parse, native call, tensor re-wrap (zipnn/zipnn.py:1072-1198)."""
+        stream = _as_stream(stream)
+        head = _peek(stream, HEADER_LEN + 1 + 9 * 255)
+        after_header = self._retrieve_header(head)
+        code = self.dtype
+        if code in (FLOAT8_E4M3FN, FLOAT8_E5M2):
+            num_buf = 1
+        elif code in (FLOAT32, FLOAT):
+            num_buf = 4
+        elif code in (BFLOAT16, FLOAT16, HALF):
+            num_buf = 2
+        elif code == UINT32:
+            raise ValueError("Unsupported uinit32 in this version yet! please try version 0.1.1")
+        else:
+            raise ValueError(f"Unsupported Dtype {self.dtype}")
+        chunk = self.compression_chunk if num_buf != 1 else min(HUF_MAX_BLOCK, self.compression_chunk)
+        n = self.original_len
+        total = stream.numel() if isinstance(stream, torch.Tensor) else stream.size
+        if total < after_header:
+            raise RuntimeError("corrupt ZipNN stream: truncated header")
+        if isinstance(stream, torch.Tensor):
+            out_u8 = _decompress_device(stream[after_header:], num_buf, self._bit_reorder, self._byte_reorder, chunk, n)
+        else:
+            out_u8 = _decompress_host(stream[after_header:], num_buf, self._bit_reorder, self._byte_reorder, chunk, n)
+
+        fmt = self.input_format
+        if fmt == EnumFormat.BYTE.value:
+            if isinstance(out_u8, torch.Tensor) and out_u8.is_cuda:
+                return out_u8
+            return memoryview(out_u8.numpy()) if isinstance(out_u8, torch.Tensor) else memoryview(out_u8)
+        tdt = torch_dtype_of_code(code)
+        t = out_u8 if isinstance(out_u8, torch.Tensor) else torch.from_numpy(out_u8)
+        if fmt == EnumFormat.TORCH.value:
+            return t.view(tdt).reshape(self.shape_bytes)
+        if fmt == EnumFormat.NUMPY.value:
+            arr = t.cpu().numpy()
+            if code in (FLOAT32, FLOAT):
+                return arr.view(np.float32).reshape(self.shape_bytes)
+            if code in (FLOAT16, HALF):
+                return arr.view(np.float16).reshape(self.shape_bytes)
+            raise ValueError(f"Unsupported Dtype {self.dtype}")
+        raise ValueError(f"Unsupported input_format {self.input_format}")
+
+
+# ---------------------------------------------------------------------- native calls
+def _as_stream(data):
+    """CUDA/CPU uint8 tensor stays a tensor if on CUDA; everything else becomes a uint8 ndarray."""
+    if isinstance(data, torch.Tensor):
+        t = data.detach().contiguous().reshape(-1)
+        t = t if t.dtype == torch.uint8 else t.view(torch.uint8)
+        return t if t.is_cuda else t.numpy()
+    return _as_u8_numpy(data)
+
+
+def _peek(stream, nbytes: int) -> bytes:
+    if isinstance(stream, torch.Tensor):
+        return stream[:nbytes].cpu().numpy().tobytes()
+    return stream[:nbytes].tobytes()
+
+
+def _cuda_stream_handle() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def _compress_device(flat_u8: torch.Tensor, header: bytes, num_buf: int, bits_mode: int, bytes_mode: int,
+                     chunk: int, threshold: float) -> torch.Tensor:
+    _native.require_cuda()
+    L = _native.lib()
+    flat_u8 = _aligned(flat_u8)
+    n = flat_u8.numel()
+    with torch.cuda.device(flat_u8.device):
+        bound = _native.compress_bound(n, num_buf, chunk, len(header))
+        out = torch.empty(bound, dtype=torch.uint8, device=flat_u8.device)
+        ws = torch.empty(_native.compress_workspace_size(n, num_buf, chunk), dtype=torch.uint8, device=flat_u8.device)
+        out_len = C.c_size_t(0)
+        hdr = (C.c_char * len(header)).from_buffer_copy(header)
+        _native.check(L.zipnn_b200_compress(flat_u8.data_ptr() if n else None, n, hdr, len(header), num_buf, bits_mode,
+                                            bytes_mode, chunk, threshold, out.data_ptr(), bound, C.byref(out_len),
+                                            ws.data_ptr(), ws.numel(), _cuda_stream_handle()))
+    return out[: out_len.value]
+
+
+def _decompress_device(body: torch.Tensor, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int,
+                       orig: int) -> torch.Tensor:
+    _native.require_cuda()
+    L = _native.lib()
+    with torch.cuda.device(body.device):
+        out = torch.empty(orig, dtype=torch.uint8, device=body.device)
+        if orig == 0:
+            return out
+        ws = torch.empty(_native.decompress_workspace_size(orig, num_buf, chunk), dtype=torch.uint8, device=body.device)
+        st = L.zipnn_b200_decompress(body.data_ptr(), body.numel(), num_buf, bits_mode, bytes_mode, chunk, orig,
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), _cuda_stream_handle(), 1)
+    if st == _native.E_CORRUPT:
+        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")  # reference: zipnn_core.c:1089
+    _native.check(st)
+    return out
+
+
+def _pinned_empty(nbytes: int) -> torch.Tensor:
+    return torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+
+
+def _host_ptr(a):
+    return a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
+
+
+def _compress_host(flat_u8, header: bytes, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int,
+                   threshold: float):
+    _native.require_cuda()
+    L = _native.lib()
+    n = flat_u8.numel() if isinstance(flat_u8, torch.Tensor) else flat_u8.size
+    bound = _native.compress_bound(n, num_buf, chunk, len(header))
+    out = _pinned_empty(bound)
+    out_len = C.c_size_t(0)
+    hdr = (C.c_char * len(header)).from_buffer_copy(header)
+    _native.check(L.zipnn_b200_compress_host(_host_ptr(flat_u8) if n else None, n, hdr, len(header), num_buf, bits_mode,
+                                             bytes_mode, chunk, threshold, out.data_ptr(), bound, C.byref(out_len)))
+    return memoryview(out.numpy()[: out_len.value])
+
+
+def _decompress_host(body: np.ndarray, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int, orig: int) -> torch.Tensor:
+    _native.require_cuda()
+    L = _native.lib()
+    out = _pinned_empty(orig)[:orig]
+    if orig == 0:
+        return out
+    body = np.ascontiguousarray(body)
+    st = L.zipnn_b200_decompress_host(body.ctypes.data, body.size, num_buf, bits_mode, bytes_mode, chunk, orig,
+                                      out.data_ptr())
+    if st == _native.E_CORRUPT:
+        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
+    _native.check(st)
+    return out
