@@ -1,0 +1,375 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the ZipNN hot path (compress + decompress) on B200.
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+prints ONE JSON line on rank 0.
+
+  step      one pass of the hot path over one batch: compress the resident tensor, then
+            decompress the stream that came out (both through zipnn_b200.ZipNN -> C ABI).
+  value     whole-job GB/s = (uncompressed bytes all ranks coded in a step) / (t_compress +
+            t_decompress), inputs resident in HBM, CUDA events, max over ranks.
+  e2e       the same metric through the host-buffer API (pinned host tensors; H2D and D2H
+            inside the timed region).
+  roofline  for the dominant kernel of the step, timed with CUDA events on its own stream.
+  cpu_baseline / --impl reference : the reference's own C path (oracle/_ref, compiled from
+            /root/reference) or, if that binary is absent, the oracle port, on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "compress+decompress GB/s on bf16 tensors"
+GIB = 1 << 30
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size-gib", type=float, default=16.0, help="uncompressed bytes per GPU")
+    ap.add_argument("--dtype", default="bfloat16")
+    ap.add_argument("--e2e-gib", type=float, default=-1.0, help="-1: size-gib if the host has the RAM, else 4")
+    ap.add_argument("--cpu-sample-gib", type=float, default=1.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ helpers
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]  # upper half = samples under load
+        return {"sm_mhz": sorted(busy)[len(busy) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_tensor(nbytes, dtype, device, seed):
+    import torch
+    esz = torch.empty(0, dtype=dtype).element_size()
+    n = nbytes // esz
+    sigma = 0.5 if esz == 1 else 0.02
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = torch.empty(n, dtype=dtype, device=device)
+    slab = 1 << 27
+    for i in range(0, n, slab):
+        m = min(slab, n - i)
+        out[i:i + m] = (torch.randn(m, generator=g, device=device, dtype=torch.float32) * sigma).to(dtype)
+    return out
+
+
+def cpu_reference_codec():
+    """-> (kind, compress(bytes, threads) -> stream, decompress(stream, n, threads))."""
+    from oracle import oracle as O
+    ref = O.ref_core()
+    hdr = bytearray(32)
+    hdr[0:2] = b"ZN"
+    if ref is not None:
+        def comp(buf, th):
+            return ref.zipnn_core(bytes(hdr), buf, 2, 1, 10, 0, 262144, 0.95, 10, th)
+
+        def dec(stream, n, th):
+            return ref.combine_dtype(memoryview(stream)[32:], 2, 1, 10, 262144, n, th)
+        return "reference", comp, dec
+    import numpy as np
+
+    def comp(buf, th):
+        return O.zipnn_compress(hdr, np.frombuffer(buf, dtype=np.uint8), 2, 1, 10, 262144, 0.95, threads=th)
+
+    def dec(stream, n, th):
+        return O.zipnn_decompress(np.asarray(stream)[32:], 2, 1, 10, 262144, n, threads=th)
+    return "port", comp, dec
+
+
+def time_cpu(sample_bytes, threads, reps=1):
+    """Round-trip GB/s of the CPU path on `sample_bytes` (bytearray; the reference rotates it in place)."""
+    kind, comp, dec = cpu_reference_codec()
+    n = len(sample_bytes)
+    best = None
+    for _ in range(reps):
+        work = bytearray(sample_bytes)  # clone outside the timed region
+        t0 = time.perf_counter()
+        s = comp(work, threads)
+        t1 = time.perf_counter()
+        d = dec(s, n, threads)
+        t2 = time.perf_counter()
+        assert len(d) == n
+        cur = (t1 - t0, t2 - t1, len(s))
+        if best is None or cur[0] + cur[1] < best[0] + best[1]:
+            best = cur
+    tc, td, slen = best
+    return kind, n / (tc + td) / 1e9, n / tc / 1e9, n / td / 1e9, slen / n
+
+
+# ------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    try:
+        import resource
+        resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+    except Exception:
+        pass
+    import torch
+    cores = os.cpu_count() or 1
+    threads = cores
+    nbytes = int(args.cpu_sample_gib * GIB)
+    t = make_tensor(nbytes, getattr(torch, args.dtype), "cpu", 1234)
+    sample = bytearray(t.view(torch.uint8).numpy().tobytes())
+    kind = "reference"
+    for _ in range(args.warmup):
+        kind, *_ = time_cpu(sample, threads)
+    t0 = time.perf_counter()
+    vals = [time_cpu(sample, threads) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    v = sum(x[1] for x in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * nbytes / (v * 1e9), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.dtype} randn*0.02 tensor, 256 KiB chunks (reference arm: {args.cpu_sample_gib} GiB sample per step)",
+                   "timing": "host wall clock; the reference C path (zipnn_core.zipnn_core + combine_dtype) called directly, input clone outside the timed region"},
+        "compress_gbs": round(sum(x[2] for x in vals) / len(vals), 4), "decompress_gbs": round(sum(x[3] for x in vals) / len(vals), 4),
+        "ratio": round(vals[0][4], 6),
+        "cpu_baseline": {"value": round(v, 4), "unit": "GB/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.cpu_sample_gib} GiB of the workload per step, {threads} threads, host has {cores} logical cores"},
+        "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": round(wall, 2),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from zipnn_b200 import ZipNN, _native
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = getattr(torch, args.dtype)
+    nbytes = int(args.size_gib * GIB)
+    t = make_tensor(nbytes, dtype, dev, 1234 + rank)
+    nbytes = t.numel() * t.element_size()
+
+    def step():
+        s = ZipNN(input_format="torch").compress(t)
+        d = ZipNN(input_format="torch").decompress(s)
+        return s, d
+
+    # ---- warm-up + exactness check (outside the timed region)
+    for _ in range(max(args.warmup, 1)):
+        s, d = step()
+    assert torch.equal(d.view(torch.uint8), t.view(torch.uint8)), "round trip is not exact"
+    stream_bytes = s.numel()
+    del s, d
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+
+    # ---- timed region: device-resident
+    clocks = ClockSampler(local_rank)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    _native.timing_enable(True)
+    launches0 = _native.launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        clocks.start()
+    ev[0].record()
+    for i in range(args.steps):
+        s = ZipNN(input_format="torch").compress(t)
+        ev[2 * i + 1].record()
+        d = ZipNN(input_format="torch").decompress(s)
+        ev[2 * i + 2].record()
+        del s, d
+    torch.cuda.synchronize()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = _native.launch_count() - launches0
+    ktimes = _native.timing_collect()
+    _native.timing_enable(False)
+    total_ms = ev[0].elapsed_time(ev[-1])
+    tc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    td_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    step_ms = total_ms / args.steps
+    if world > 1:
+        tt = torch.tensor([step_ms, tc_ms, td_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_ms, tc_ms, td_ms = [float(x) for x in tt.tolist()]
+    value = world * nbytes / (step_ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the public API (rank-local; reported for the whole job)
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        want = args.e2e_gib if args.e2e_gib > 0 else (args.size_gib if psutil.virtual_memory().available > (6 * args.size_gib + 16) * GIB * world else min(4.0, args.size_gib))
+        eb = int(want * GIB)
+        torch.cuda.empty_cache()
+        ht = torch.empty(eb // t.element_size(), dtype=dtype, pin_memory=True)
+        ht.copy_(t[: ht.numel()])
+        torch.cuda.synchronize()
+        zs = ZipNN(input_format="torch").compress(ht)         # warm-up (pins the result buffers, sizes the device cache)
+        hd = ZipNN(input_format="torch").decompress(zs)
+        assert torch.equal(hd.view(torch.uint8), ht.view(torch.uint8))
+        c_e2e = len(zs)
+        del zs, hd
+        reps = max(2, min(args.steps, 3))
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            zs = ZipNN(input_format="torch").compress(ht)     # H2D N, kernels, D2H C
+            hd = ZipNN(input_format="torch").decompress(zs)   # H2D C, kernels, D2H N
+            _ = hd[0].item()                                  # read the result on the host
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3 / reps
+        if world > 1:
+            tt = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_ms = float(tt.item())
+        e2e = {"value": round(world * eb / (e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": world * (eb + c_e2e),
+               "d2h_bytes_per_step": world * (c_e2e + eb), "ms_per_step": round(e_ms, 2), "bytes_per_gpu": eb,
+               "api": "zipnn_b200.ZipNN(input_format='torch').compress(cpu pinned tensor) / .decompress(host stream) -> zipnn_b200_compress_host / zipnn_b200_decompress_host"}
+        del ht
+
+    # ---- CPU baseline beside it (rank 0, single-GPU runs only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            import resource
+            resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+        except Exception:
+            pass
+        sb = int(min(args.cpu_sample_gib * GIB, nbytes))
+        sample = bytearray(t.view(torch.uint8)[:sb].cpu().numpy().tobytes())
+        cores = os.cpu_count() or 1
+        kind, v, vc, vd, ratio_cpu = time_cpu(sample, cores, reps=2)
+        cpu = {"value": round(v, 4), "unit": "GB/s", "cores": cores, "kind": kind, "compress_gbs": round(vc, 4),
+               "decompress_gbs": round(vd, 4), "ratio": round(ratio_cpu, 6),
+               "sample": f"first {sb / GIB:.2f} GiB of the same tensor, {cores} threads (all logical cores), best of 2"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = peaks()
+    per_launch = {k: (ms / max(cnt, 1), cnt) for k, (ms, cnt) in ktimes.items() if cnt}
+    dom = max(per_launch, key=lambda k: per_launch[k][0] * per_launch[k][1])
+    N, Cb = nbytes, stream_bytes
+    G = 1 if t.element_size() == 1 else (2 if t.element_size() == 2 else 4)
+    huf_payload = Cb - (N // G) * (G - 1) if G > 1 else Cb  # bytes of the Huffman-coded group(s) (the others are stored raw)
+    algo = {  # algorithmic bytes per launch, see DESIGN.md "kernels"
+        "k_encode_stats": N,                    # reads every input byte once
+        "k_encode_write": N + Cb,               # reads the input again, writes the stream
+        "k_huf_decode": huf_payload + N // G,   # reads the coded planes, writes them decoded (planar)
+        "k_regroup": (Cb - huf_payload) + N // G + N,  # raw planes from the stream + decoded planes -> elements
+    }
+    dom_ms = per_launch[dom][0]
+    achieved = algo.get(dom, N) / (dom_ms * 1e-3) / 1e9
+    kernels = {k: {"ms_per_launch": round(v[0], 4), "launches": v[1],
+                   "algo_gbs": round(algo[k] / (v[0] * 1e-3) / 1e9, 1) if k in algo and v[0] > 0 else None}
+               for k, v in per_launch.items()}
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"synthetic {args.dtype} tensor, {nbytes / GIB:.2f} GiB per GPU, randn*0.02 (seed 1234+rank), 256 KiB chunks; "
+                               "step = ZipNN.compress(cuda tensor) + ZipNN.decompress(stream), byte-exact round trip verified before timing",
+                   "l2": "inputs are far larger than the 126 MB L2 (no flush needed)", "sharding": "one tensor shard per GPU, no data-path collective"},
+        "compress_gbs": round(world * N / (tc_ms * 1e-3) / 1e9, 2), "decompress_gbs": round(world * N / (td_ms * 1e-3) / 1e9, 2),
+        "ratio": round(Cb / N, 6),
+        "path_roofline": {"compress_frac": round((N + Cb) / (tc_ms * 1e-3) / 1e9 / peak, 4),
+                          "decompress_frac": round((N + Cb) / (td_ms * 1e-3) / 1e9 / peak, 4),
+                          "note": "(N + C) / t / peak: SURVEY.md section 8d definition for the whole direction"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo.get(dom, N), "ms_per_launch": round(dom_ms, 4)},
+        "kernels": kernels,
+        "gpu_launches": int(launches),
+        "clocks": clk,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

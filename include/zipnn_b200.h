@@ -110,6 +110,17 @@ int zipnn_b200_decompress_host(const void* h_body, size_t body_len, int num_buf,
 /* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
 unsigned long long zipnn_b200_launch_count(void);
 
+/* ---- optional per-kernel timing (the reference has only commented-out gettimeofday prints,
+ * csrc/zipnn_core.c:409-410,562-566) ---------------------------------------------------------
+ * When enabled, every kernel launch is bracketed by CUDA events on its own stream.
+ * zipnn_b200_timing_collect synchronises the device, adds the elapsed milliseconds and launch
+ * counts per kernel id into the caller's arrays (length >= zipnn_b200_timing_kernel_count())
+ * and clears the log. */
+void zipnn_b200_timing_enable(int on);
+int zipnn_b200_timing_kernel_count(void);
+const char* zipnn_b200_timing_kernel_name(int id);
+int zipnn_b200_timing_collect(double* ms_total, unsigned long long* launches, int n);
+
 #ifdef __cplusplus
 }
 #endif

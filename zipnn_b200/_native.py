@@ -73,6 +73,10 @@ def lib() -> C.CDLL:
                 "zipnn_b200_regroup": (i32, [vp, sz, sz, i32, i32, vp, vp]),
                 "zipnn_b200_compress_host": (i32, [vp, sz, vp, sz, i32, i32, i32, sz, C.c_float, vp, sz, szp]),
                 "zipnn_b200_decompress_host": (i32, [vp, sz, i32, i32, i32, sz, sz, vp]),
+                "zipnn_b200_timing_enable": (None, [i32]),
+                "zipnn_b200_timing_kernel_count": (i32, []),
+                "zipnn_b200_timing_kernel_name": (C.c_char_p, [i32]),
+                "zipnn_b200_timing_collect": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_ulonglong), i32]),
             }
             for name, (res, args) in sig.items():
                 f = getattr(L, name)
@@ -86,6 +90,8 @@ EXPORTS = [
     "zipnn_b200_launch_count", "zipnn_b200_compress_bound", "zipnn_b200_compress_workspace_size",
     "zipnn_b200_decompress_workspace_size", "zipnn_b200_compress", "zipnn_b200_decompress",
     "zipnn_b200_split", "zipnn_b200_regroup", "zipnn_b200_compress_host", "zipnn_b200_decompress_host",
+    "zipnn_b200_timing_enable", "zipnn_b200_timing_kernel_count", "zipnn_b200_timing_kernel_name",
+    "zipnn_b200_timing_collect",
 ]
 
 
@@ -127,3 +133,17 @@ def decompress_workspace_size(orig: int, num_buf: int, chunk: int) -> int:
 
 def launch_count() -> int:
     return int(lib().zipnn_b200_launch_count())
+
+
+def timing_enable(on: bool) -> None:
+    lib().zipnn_b200_timing_enable(1 if on else 0)
+
+
+def timing_collect() -> dict:
+    """-> {kernel name: (total ms, launches)} since the last collect; synchronises the device."""
+    L = lib()
+    k = L.zipnn_b200_timing_kernel_count()
+    ms = (C.c_double * k)()
+    cnt = (C.c_ulonglong * k)()
+    check(L.zipnn_b200_timing_collect(ms, cnt, k))
+    return {L.zipnn_b200_timing_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(k)}

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "decode.cuh"
@@ -38,6 +39,53 @@ inline bool cuda_ok(cudaError_t e) {
     g_launches.fetch_add(1, std::memory_order_relaxed);     \
     if (!cuda_ok(cudaGetLastError())) return ZIPNN_B200_E_CUDA; \
   } while (0)
+
+// ---- optional per-kernel timing (CUDA events on the launching stream) ----------------
+// Off by default.  bench.py turns it on to attribute the step time to kernels; the events
+// sit between launches on the same stream, so they do not change the schedule.
+enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKRegroup, kKEncodeStats, kKEncodeScan, kKEncodeWrite, kKSplit,
+                kKRegroupPlanar, kKCount };
+const char* const kKernelNames[kKCount] = {"k_decode_meta", "k_huf_decode", "k_regroup", "k_encode_stats",
+                                           "k_encode_scan", "k_encode_write", "k_split_planar", "k_regroup_planar"};
+struct TimedSpan {
+  int id;
+  cudaEvent_t a, b;
+};
+std::atomic<int> g_timing{0};
+std::mutex g_timing_mu;
+std::vector<TimedSpan> g_spans;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t take_event() {
+  cudaEvent_t e = nullptr;
+  if (!g_event_pool.empty()) {
+    e = g_event_pool.back();
+    g_event_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+struct ScopedTimer {
+  int id;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr;
+  ScopedTimer(int id_, cudaStream_t st_) : id(id_), st(st_) {
+    if (g_timing.load(std::memory_order_relaxed)) {
+      std::lock_guard<std::mutex> lk(g_timing_mu);
+      a = take_event();
+      cudaEventRecord(a, st);
+    }
+  }
+  ~ScopedTimer() {
+    if (a) {
+      std::lock_guard<std::mutex> lk(g_timing_mu);
+      cudaEvent_t b = take_event();
+      cudaEventRecord(b, st);
+      g_spans.push_back({id, a, b});
+    }
+  }
+};
 
 int sm_count_cached() {
   static int cached = 0;
@@ -118,6 +166,40 @@ int zipnn_b200_last_cuda_error(void) { return g_last_cuda_error.load(); }
 int zipnn_b200_sm_count(void) { return sm_count_cached(); }
 unsigned long long zipnn_b200_launch_count(void) { return g_launches.load(); }
 
+void zipnn_b200_timing_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing.store(on ? 1 : 0);
+  for (auto& sp : g_spans) {
+    g_event_pool.push_back(sp.a);
+    g_event_pool.push_back(sp.b);
+  }
+  g_spans.clear();
+}
+
+int zipnn_b200_timing_kernel_count(void) { return kKCount; }
+const char* zipnn_b200_timing_kernel_name(int id) { return (id >= 0 && id < kKCount) ? kKernelNames[id] : ""; }
+
+int zipnn_b200_timing_collect(double* ms_total, unsigned long long* launches, int n) {
+  if (!ms_total || !launches || n < kKCount) return ZIPNN_B200_E_ARG;
+  ZB_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int i = 0; i < n; i++) {
+    ms_total[i] = 0;
+    launches[i] = 0;
+  }
+  for (auto& sp : g_spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+      ms_total[sp.id] += ms;
+      launches[sp.id] += 1;
+    }
+    g_event_pool.push_back(sp.a);
+    g_event_pool.push_back(sp.b);
+  }
+  g_spans.clear();
+  return ZIPNN_B200_OK;
+}
+
 int zipnn_b200_compress_bound(size_t n, int num_buf, size_t chunk, size_t hdr_len, size_t* out) {
   if (!out || chunk == 0 || !(num_buf == 1 || num_buf == 2 || num_buf == 4)) return ZIPNN_B200_E_ARG;
   *out = hdr_len + 9 * (size_t)num_buf * num_chunks(n, chunk) + n;
@@ -154,12 +236,14 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   {
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((nitems + threads - 1) / threads, 4096);
+    ScopedTimer tm(kKDecodeMeta, st);
     k_decode_meta<<<blocks, threads, 0, st>>>(body, body_len, G, K, (uint32_t)chunk, orig, ctrl, items);
     ZB_LAUNCHED();
   }
   {
     const uint64_t warps = (nitems + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
+    ScopedTimer tm(kKHufDecode, st);
     k_huf_decode_planar<<<(unsigned)warps, 32, sizeof(DecodeSmem), st>>>(body, body_len, items, nitems, planes,
                                                                          L.pstride, ctrl);
     ZB_LAUNCHED();
@@ -168,6 +252,7 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     const uint32_t tiles_per_chunk = (uint32_t)((chunk + kMergeTile - 1) / kMergeTile);
     const uint64_t ntiles = K * tiles_per_chunk;
     const int blocks = (int)std::min<uint64_t>(ntiles, (uint64_t)sm_count_cached() * 16);
+    ScopedTimer tm(kKRegroup, st);
     int rc = dispatch_G(G, [&](auto g) -> int {
       k_regroup<decltype(g)::value><<<blocks, kMergeThreads, 0, st>>>(body, items, K, planes, L.pstride, (uint32_t)chunk,
                                                                       orig, bits_mode, (uint8_t*)d_out);
@@ -190,6 +275,7 @@ int zipnn_b200_split(const void* d_in, size_t n, int num_buf, int bits_mode, voi
   const uint64_t units = n / (16ull * num_buf);
   const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((units + kStage1Threads - 1) / kStage1Threads,
                                                                     (uint64_t)sm_count_cached() * 32));
+  ScopedTimer tm(kKSplit, st);
   return dispatch_G(num_buf, [&](auto g) -> int {
     k_split_planar<decltype(g)::value><<<blocks, kStage1Threads, 0, st>>>((const uint8_t*)d_in, n, bits_mode,
                                                                           (uint8_t*)d_planes, stride);
@@ -208,6 +294,7 @@ int zipnn_b200_regroup(const void* d_planes, size_t stride, size_t n, int num_bu
   const uint64_t units = n / (16ull * num_buf);
   const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((units + kStage1Threads - 1) / kStage1Threads,
                                                                     (uint64_t)sm_count_cached() * 32));
+  ScopedTimer tm(kKRegroupPlanar, st);
   return dispatch_G(num_buf, [&](auto g) -> int {
     k_regroup_planar<decltype(g)::value><<<blocks, kStage1Threads, 0, st>>>((const uint8_t*)d_planes, stride, n,
                                                                             bits_mode, (uint8_t*)d_out);
