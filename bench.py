@@ -324,8 +324,7 @@ def run_ours(args, rank, local_rank, world):
     algo = {  # algorithmic bytes per launch, see DESIGN.md "kernels"
         "k_encode_stats": N,                    # reads every input byte once
         "k_encode_write": N + Cb,               # reads the input again, writes the stream
-        "k_huf_decode": huf_payload + N // G,   # reads the coded planes, writes them decoded (planar)
-        "k_regroup": (Cb - huf_payload) + N // G + N,  # raw planes from the stream + decoded planes -> elements
+        "k_huf_decode_fused": Cb + N,           # reads the whole stream, writes the elements (fused decode + regroup)
     }
     dom_ms = per_launch[dom][0]
     achieved = algo.get(dom, N) / (dom_ms * 1e-3) / 1e9

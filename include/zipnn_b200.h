@@ -59,7 +59,12 @@ int zipnn_b200_sm_count(void);                /* multiprocessor count of the cur
 /* Upper bound of the whole stream (python header included). */
 int zipnn_b200_compress_bound(size_t n, int num_buf, size_t chunk, size_t hdr_len, size_t* out);
 int zipnn_b200_compress_workspace_size(size_t n, int num_buf, size_t chunk, size_t* out);
+/* Decompress workspace.  The normal size covers streams in which every chunk has at most one
+ * Huffman-coded byte group (what float tensors produce) plus 64 chunks of the general kind;
+ * if a stream needs more, zipnn_b200_decompress returns ZIPNN_B200_E_CAPACITY and the caller
+ * retries with the `_full` size. */
 int zipnn_b200_decompress_workspace_size(size_t orig, int num_buf, size_t chunk, size_t* out);
+int zipnn_b200_decompress_workspace_size_full(size_t orig, int num_buf, size_t chunk, size_t* out);
 
 /* ---- device-resident buffers ------------------------------------------------- */
 /*

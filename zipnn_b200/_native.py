@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
                 "zipnn_b200_compress_bound": (i32, [sz, i32, sz, sz, szp]),
                 "zipnn_b200_compress_workspace_size": (i32, [sz, i32, sz, szp]),
                 "zipnn_b200_decompress_workspace_size": (i32, [sz, i32, sz, szp]),
+                "zipnn_b200_decompress_workspace_size_full": (i32, [sz, i32, sz, szp]),
                 "zipnn_b200_compress": (i32, [vp, sz, vp, sz, i32, i32, i32, sz, C.c_float, vp, sz, szp, vp, sz, vp]),
                 "zipnn_b200_decompress": (i32, [vp, sz, i32, i32, i32, sz, sz, vp, vp, sz, vp, i32]),
                 "zipnn_b200_split": (i32, [vp, sz, i32, i32, vp, sz, vp]),
@@ -88,7 +89,8 @@ def lib() -> C.CDLL:
 EXPORTS = [
     "zipnn_b200_version", "zipnn_b200_strerror", "zipnn_b200_last_cuda_error", "zipnn_b200_sm_count",
     "zipnn_b200_launch_count", "zipnn_b200_compress_bound", "zipnn_b200_compress_workspace_size",
-    "zipnn_b200_decompress_workspace_size", "zipnn_b200_compress", "zipnn_b200_decompress",
+    "zipnn_b200_decompress_workspace_size", "zipnn_b200_decompress_workspace_size_full", "zipnn_b200_compress",
+    "zipnn_b200_decompress",
     "zipnn_b200_split", "zipnn_b200_regroup", "zipnn_b200_compress_host", "zipnn_b200_decompress_host",
     "zipnn_b200_timing_enable", "zipnn_b200_timing_kernel_count", "zipnn_b200_timing_kernel_name",
     "zipnn_b200_timing_collect",
@@ -125,9 +127,10 @@ def compress_workspace_size(n: int, num_buf: int, chunk: int) -> int:
     return out.value
 
 
-def decompress_workspace_size(orig: int, num_buf: int, chunk: int) -> int:
+def decompress_workspace_size(orig: int, num_buf: int, chunk: int, full: bool = False) -> int:
     out = C.c_size_t(0)
-    check(lib().zipnn_b200_decompress_workspace_size(orig, num_buf, chunk, C.byref(out)))
+    f = lib().zipnn_b200_decompress_workspace_size_full if full else lib().zipnn_b200_decompress_workspace_size
+    check(f(orig, num_buf, chunk, C.byref(out)))
     return out.value
 
 

@@ -1,136 +1,257 @@
-// decode.cuh -- decompress side:  stream metadata -> item table, Huffman bit-unpack,
-// byte-group regroup (+ sign-bit un-rotate).
+// decode.cuh -- decompress side:  stream metadata -> item table, Huffman bit-unpack fused
+// with byte-group regroup (+ sign-bit un-rotate).
 //
 // Replaces reference csrc/zipnn_core.c:881-1142 (py_combine_dtype), :768-861
 // (decompression_chunk_worker), huf_decompress.c:118-354 (table + 4-stream decode),
 // data_manipulation_dtype16.c:167-216 and data_manipulation_dtype32.c:391-456 (combine).
+//
+// Kernels
+//   k_decode_meta        one thread per chunk: item table, per-chunk mode, RLE fill blocks
+//   k_huf_decode_fused   chunks with exactly one Huffman-coded group (the normal case:
+//                        the exponent plane) -> decoded, merged with the raw/RLE planes,
+//                        un-rotated and written as elements, in one pass
+//   k_huf_decode_planar  chunks with several Huffman-coded groups, or a ragged last chunk:
+//                        decode each coded plane into a workspace plane ...
+//   k_regroup            ... and regroup planes (raw / RLE / workspace) into elements; also
+//                        handles chunks with no coded group at all
 #pragma once
 #include "common.cuh"
 
 namespace zb {
 
+enum : uint32_t { kModePlain = 0, kModeFused = 1, kModeGeneral = 2 };
+constexpr uint32_t kFillBytes = 64;  // replicated RLE byte block per item (read with stride 0)
+
+struct DecodeCfg {
+  const uint8_t* body;
+  uint64_t body_len;
+  int G;
+  uint64_t K;
+  uint32_t chunk;
+  uint64_t orig;
+  int bits_mode;
+  Ctrl* ctrl;
+  ItemDesc* items;      // [G*K]
+  uint8_t* mode;        // [K]
+  uint32_t* slot;       // [K] workspace plane slot of a general-mode chunk (G planes per slot)
+  uint8_t* fill;        // [G*K*kFillBytes]
+  uint8_t* planes;      // [slots][G][pstride]
+  uint64_t pstride;
+  uint32_t max_slots;
+};
+
 // ====================================================================================
-// Kernel 1: parse + validate the per-(group,chunk) metadata, emit the item table.
+// Kernel 1: parse + validate the per-(group,chunk) metadata.
 // Stream body layout (csrc/zipnn_core.c:105-244):
 //   types u8[G][K] | cum u64le[G][K] (inclusive, per group) | group-major payload
 // ====================================================================================
-__global__ void k_decode_meta(const uint8_t* __restrict__ body, uint64_t body_len, int G, uint64_t K,
-                              uint32_t chunk, uint64_t orig, Ctrl* ctrl, ItemDesc* items) {
+__global__ void k_decode_meta(DecodeCfg cfg) {
+  const int G = cfg.G;
+  const uint64_t K = cfg.K;
   const uint64_t nitems = (uint64_t)G * K;
-  const uint8_t* types = body;
-  const uint8_t* cum = body + nitems;
+  const uint8_t* types = cfg.body;
+  const uint8_t* cum = cfg.body + nitems;
   const uint64_t payload0 = 9 * nitems;
-  const uint64_t payload_len = body_len - payload0;
+  const uint64_t payload_len = cfg.body_len - payload0;
   uint64_t base[4] = {0, 0, 0, 0};
   for (int g = 1; g < G; g++) base[g] = base[g - 1] + ld_u64_bytes(cum + 8 * ((uint64_t)(g - 1) * K + (K - 1)));
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int g = 0; g < 4; g++) ctrl->base[g] = payload0 + base[g];
-    uint64_t all = base[G - 1] + ld_u64_bytes(cum + 8 * ((uint64_t)(G - 1) * K + (K - 1)));
-    if (all > payload_len) atomicOr(&ctrl->error, kErrCorrupt);
+    for (int g = 0; g < 4; g++) cfg.ctrl->base[g] = payload0 + base[g];
+    const uint64_t all = base[G - 1] + ld_u64_bytes(cum + 8 * ((uint64_t)(G - 1) * K + (K - 1)));
+    if (all > payload_len) atomicOr(&cfg.ctrl->error, kErrCorrupt);
   }
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nitems;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i / K);
-    const uint64_t c = i - (uint64_t)g * K;
-    const uint64_t hi = ld_u64_bytes(cum + 8 * i);
-    const uint64_t lo = c ? ld_u64_bytes(cum + 8 * (i - 1)) : 0;
-    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(orig - c * (uint64_t)chunk) : chunk;
-    const uint32_t dlen = plane_len(chunk_len, G, g);
-    const uint8_t type = types[i];
-    ItemDesc d;
-    d.src_off = payload0 + base[g] + lo;
-    d.dec_len = dlen;
-    d.pad = 0;
-    bool bad = (hi < lo) || (base[g] + hi > payload_len) || (type > 1) || (hi - lo > 0xFFFFFFFFull);
-    const uint32_t slen = (uint32_t)(hi - lo);
-    d.src_len = slen;
-    if (type == 0) {
-      d.kind = kRaw;
-      bad = bad || (slen != dlen);
-    } else {
-      // HUF_decompress (huf_decompress.c:1056-1081): csize > dst -> error; == -> copy; 1 -> RLE
-      if (dlen == 0) {
-        d.kind = kRaw;  // the reference never decodes an empty plane
-        d.src_len = 0;
-      } else if (slen > dlen || slen == 0) {
-        bad = true;
+  for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < K; c += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)cfg.chunk) : cfg.chunk;
+    int nhuf = 0;
+    bool bad_chunk = false;
+    for (int g = 0; g < G; g++) {
+      const uint64_t i = (uint64_t)g * K + c;
+      const uint64_t hi = ld_u64_bytes(cum + 8 * i);
+      const uint64_t lo = c ? ld_u64_bytes(cum + 8 * (i - 1)) : 0;
+      const uint32_t dlen = plane_len(chunk_len, G, g);
+      const uint8_t type = types[i];
+      ItemDesc d;
+      d.src_off = payload0 + base[g] + lo;
+      d.dec_len = dlen;
+      d.pad = 0;
+      bool bad = (hi < lo) || (base[g] + hi > payload_len) || (type > 1) || (hi - lo > 0xFFFFFFFFull);
+      const uint32_t slen = (uint32_t)(hi - lo);
+      d.src_len = slen;
+      if (type == 0) {
         d.kind = kRaw;
-      } else if (slen == dlen) {
-        d.kind = kRaw;
-      } else if (slen == 1) {
-        d.kind = kRle;
+        bad = bad || (slen != dlen);
       } else {
-        d.kind = kHuf;
-        bad = bad || (dlen > (uint32_t)kHufBlockMax);
+        // HUF_decompress (huf_decompress.c:1056-1081): csize > dst -> error; == -> copy; 1 -> RLE
+        if (dlen == 0) {
+          d.kind = kRaw;
+          d.src_len = 0;
+        } else if (slen > dlen || slen == 0) {
+          bad = true;
+          d.kind = kRaw;
+        } else if (slen == dlen) {
+          d.kind = kRaw;
+        } else if (slen == 1) {
+          d.kind = kRle;
+        } else {
+          d.kind = kHuf;
+          bad = bad || (dlen > (uint32_t)kHufBlockMax);
+        }
+      }
+      if (bad) {
+        atomicOr(&cfg.ctrl->error, kErrCorrupt);
+        d.kind = kRaw;
+        d.src_len = 0;
+        d.dec_len = 0;
+        bad_chunk = true;
+      }
+      if (d.kind == kHuf) nhuf++;
+      if (d.kind == kRle) {
+        const uint32_t v = 0x01010101u * (uint32_t)cfg.body[d.src_off];
+        uint4* f = reinterpret_cast<uint4*>(cfg.fill + i * kFillBytes);
+#pragma unroll
+        for (int q = 0; q < (int)(kFillBytes / 16); q++) f[q] = make_uint4(v, v, v, v);
+      }
+      cfg.items[i] = d;
+    }
+    // The fused kernel wants whole, equally long planes whose quarter streams start on
+    // 16-element boundaries: chunk_len a multiple of 64*G.  Anything else goes the general way.
+    uint32_t m = kModePlain;
+    if (bad_chunk) {
+      m = kModePlain;
+    } else if (nhuf == 1 && (chunk_len % (64u * (uint32_t)G)) == 0) {
+      m = kModeFused;
+    } else if (nhuf >= 1) {
+      m = kModeGeneral;
+      const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
+      if (s >= cfg.max_slots) {
+        atomicOr(&cfg.ctrl->error, kErrWorkspace);
+        m = kModePlain;
+        for (int g = 0; g < G; g++) {  // neutralise: nothing will decode this chunk
+          cfg.items[(uint64_t)g * K + c].kind = kRaw;
+          cfg.items[(uint64_t)g * K + c].dec_len = 0;
+        }
+      } else {
+        cfg.slot[c] = s;
       }
     }
-    if (bad) {
-      atomicOr(&ctrl->error, kErrCorrupt);
-      d.kind = kRaw;
-      d.src_len = 0;
-      d.dec_len = 0;
-    }
-    items[i] = d;
+    cfg.mode[c] = (uint8_t)m;
   }
 }
 
 // ====================================================================================
-// Kernel 2: Huffman decode of kHuf items into planar byte planes.
+// Shared pieces of the two Huffman kernels.
 //
 // One thread per bitstream (a huff0 block is 4 independent backward bitstreams,
-// huf_decompress.c:283-298), one warp = 8 items.  Each item's single-symbol decode table
-// (2^tableLog x {symbol, length}) lives in shared memory; the stream is read through a
-// left-aligned 64-bit window refilled one aligned 32-bit word at a time with the next
-// word prefetched, so the global-load latency is off the symbol-to-symbol chain.
+// huf_decompress.c:283-298); one warp = 8 blocks.  Each block's single-symbol decode
+// table (2^tableLog x {symbol, length}) lives in shared memory.
+//
+// Stream bytes reach the thread through a private 128-byte ring in shared memory that is
+// filled with cp.async (16-byte, L2-only) two iterations ahead of use.  Registers never
+// wait on a global load: a per-lane "prefetch into a register" does not work on a GPU,
+// because lanes refill at different symbols while the scoreboard is per warp, so every
+// refill ends up waiting for some other lane's load (measured: 234 clk/symbol).
+// The refill itself is branch-free: every second symbol all lanes execute the same
+// select/shift/LDS sequence, whether or not their window needed a word.
 // ====================================================================================
 constexpr int kDecItemsPerWarp = 8;
 constexpr int kDecLutLog = 11;  // the reference encoder never exceeds 11 (HUF_TABLELOG_DEFAULT)
 constexpr int kDecLutEntries = 1 << kDecLutLog;
+constexpr uint32_t kRingBytes = 128;
 
 struct DecodeSmem {
   uint16_t lut[kDecItemsPerWarp][kDecLutEntries];  // also scratch for the table parse
-  uint8_t weights[kDecItemsPerWarp][256];
+  __align__(16) uint8_t ring[32][kRingBytes];      // per lane; weights[8][256] alias it during the parse
 };
 static_assert(sizeof(FseDec) <= sizeof(uint16_t) * kDecLutEntries, "FseDec must fit in one LUT slot");
+static_assert(32 * kRingBytes >= kDecItemsPerWarp * 256, "weights alias the ring");
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 struct BitWindow {
-  uint64_t w;           // unread bits, left aligned
-  int avail;            // valid bits in w
-  const uint32_t* wp;   // next word to prefetch (moves down)
-  uint32_t nxt;         // prefetched word
-  const uint32_t* wp0;  // wp right after init (for the exact-consumption check)
-  int loaded0;          // bits in the window right after init
-  uint32_t unread;      // bits between stream start and the end mark
+  uint64_t w;            // unread bits, left aligned
+  int avail;             // valid bits in w
+  uint32_t nxt;          // the word at `wp` (next to append)
+  uint32_t wp;           // byte offset (from gbase) of the next word to append; moves down
+  uint32_t fetch;        // byte offset (from gbase) of the lowest 16-byte block already requested
+  uint32_t wp0;          // wp right after init (for the exact-consumption check)
+  int loaded0;           // bits in the window right after init
+  uint32_t unread;       // bits between stream start and the end mark
+  const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
+  uint32_t floor_off;    // do not request blocks below this offset (start of the stream buffer)
+  uint8_t* ring;
 };
 
-__device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo,
-                                            const uint8_t* hi) {
+__device__ __forceinline__ uint32_t ring_word(const BitWindow& b, uint32_t off) {
+  return *reinterpret_cast<const uint32_t*>(b.ring + (off & (kRingBytes - 1)));
+}
+
+// Request every 16-byte block that fits in the ring below what is still needed (<= `maxn`).
+__device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
+#pragma unroll 2
+  for (int i = 0; i < maxn; i++) {
+    const uint32_t f = b.fetch - 16;
+    // block [f, f+16) may overwrite ring bytes only if they are above everything still needed
+    // (the word at wp and the one above it): f + ring > wp + 8
+    if (b.fetch >= 16 + b.floor_off && f + kRingBytes > b.wp + 8) {
+      cp_async16(b.ring + (f & (kRingBytes - 1)), b.gbase + f);
+      b.fetch = f;
+    }
+  }
+}
+
+// s points at the stream (len bytes); lo/hi bound the buffer that may be read.
+__device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo, uint8_t* ring) {
   const uint8_t lastb = s[len - 1];
   if (lastb == 0) return false;
-  const uint64_t mark = 8ull * (uint64_t)(uintptr_t)(s + len - 1) + (uint64_t)hb32(lastb);  // end-mark bit
-  b.unread = (uint32_t)(mark - 8ull * (uint64_t)(uintptr_t)s);
+  b.ring = ring;
+  b.gbase = reinterpret_cast<const uint8_t*>((uintptr_t)(s) & ~(uintptr_t)(kRingBytes - 1));
+  if (b.gbase < lo) {
+    // keep offsets non-negative relative to a base that is still 128-aligned
+    b.floor_off = (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15);
+  } else {
+    b.floor_off = 0;
+    // never read more than one ring below the item: those bytes are not needed
+  }
+  const uint32_t s_off = (uint32_t)((uintptr_t)s - (uintptr_t)b.gbase);
+  const uint32_t mark = 8u * (s_off + len - 1) + (uint32_t)hb32(lastb);  // bit offset of the end mark
+  b.unread = mark - 8u * s_off;
   if (b.unread == 0) return false;
-  const uintptr_t top_byte = (uintptr_t)((mark - 1) >> 3);
-  const uint32_t* wt = reinterpret_cast<const uint32_t*>(top_byte & ~(uintptr_t)3);
-  const int k = (int)(mark - 8ull * (uint64_t)(uintptr_t)wt);  // 1..32 unread bits in the top word
-  const uint32_t topw = ld_word_guarded(wt, lo, hi);
-  const uint32_t low1 = ld_word_guarded(wt - 1, lo, hi);
+  const uint32_t top_word = ((mark - 1) >> 3) & ~3u;       // offset of the word holding the top unread bit
+  const int k = (int)(mark - 8u * top_word);                // 1..32 unread bits in it
+  b.fetch = (top_word & ~15u) + 16;
+  b.wp = top_word;
+  ring_top_up(b, (int)(kRingBytes / 16));
+  cp_async_commit();
+  cp_async_wait<0>();
+  const uint32_t topw = ring_word(b, top_word);
+  const uint32_t low1 = (top_word >= 4) ? ring_word(b, top_word - 4) : 0u;
   b.w = ((uint64_t)(topw << (32 - k)) << 32) | ((uint64_t)low1 << (32 - k));
   b.avail = k + 32;
   b.loaded0 = k + 32;
-  b.nxt = ld_word_guarded(wt - 2, lo, hi);
-  b.wp = wt - 3;
+  b.wp = top_word - 8;
   b.wp0 = b.wp;
+  b.nxt = ring_word(b, b.wp);
   return true;
 }
 
-__device__ __forceinline__ void window_refill(BitWindow& b, const uint8_t* lo_aligned) {
-  if (b.avail <= 32) {
-    b.w |= (uint64_t)b.nxt << (32 - b.avail);
-    b.avail += 32;
-    b.nxt = (reinterpret_cast<const uint8_t*>(b.wp) >= lo_aligned) ? __ldg(b.wp) : 0u;
-    b.wp--;
-  }
+// Branch-free: append `nxt` if the window has room for a whole word, then re-read the
+// word at (the possibly moved) wp.  Call at least every 2 symbols (2 x 11 bits <= 32).
+__device__ __forceinline__ void window_refill(BitWindow& b) {
+  const bool need = b.avail <= 32;
+  const uint32_t v = need ? b.nxt : 0u;
+  const int sh = need ? (32 - b.avail) : 0;
+  b.w |= (uint64_t)v << sh;
+  b.avail += need ? 32 : 0;
+  b.wp -= need ? 4u : 0u;
+  b.nxt = ring_word(b, b.wp);
 }
 
 __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const uint16_t* lut, int lg) {
@@ -141,32 +262,33 @@ __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const uint16_t* 
   return e & 0xFFu;
 }
 
-// Decode `count` symbols of one stream into dst (global).  Returns false if the stream
-// was not consumed exactly.
-__device__ __forceinline__ bool decode_stream_planar(BitWindow& b, const uint16_t* lut, int lg, uint8_t* dst,
-                                                     uint32_t count, const uint8_t* lo_aligned) {
-  uint32_t done = 0;
-  if ((((uintptr_t)dst) & 15) == 0) {
-    const uint32_t n16 = count >> 4;
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (uint32_t it = 0; it < n16; it++) {
-      uint32_t o[4] = {0, 0, 0, 0};
+// 16 symbols -> 4 words (symbol j in byte j).  Ring maintenance for the NEXT iterations is
+// issued first so the copies overlap the decode.
+__device__ __forceinline__ void decode16(BitWindow& b, const uint16_t* lut, int lg, uint32_t (&o)[4]) {
+  ring_top_up(b, 2);
+  cp_async_commit();
+  o[0] = o[1] = o[2] = o[3] = 0;
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        window_refill(b, lo_aligned);
-        o[j >> 2] |= window_decode(b, lut, lg) << (8 * (j & 3));
-        o[(j + 1) >> 2] |= window_decode(b, lut, lg) << (8 * ((j + 1) & 3));
-      }
-      d4[it] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-    done = n16 << 4;
+  for (int j = 0; j < 16; j += 2) {
+    window_refill(b);
+    o[j >> 2] |= window_decode(b, lut, lg) << (8 * (j & 3));
+    o[(j + 1) >> 2] |= window_decode(b, lut, lg) << (8 * ((j + 1) & 3));
   }
-  for (; done < count; done++) {
-    window_refill(b, lo_aligned);
-    dst[done] = (uint8_t)window_decode(b, lut, lg);
-  }
-  const int refills = (int)(b.wp0 - b.wp);
-  const int consumed = b.loaded0 + 32 * refills - b.avail;
+  cp_async_wait<1>();  // everything but the group just committed has landed
+}
+
+__device__ __forceinline__ uint32_t decode1(BitWindow& b, const uint16_t* lut, int lg) {
+  ring_top_up(b, 1);
+  cp_async_commit();
+  window_refill(b);
+  const uint32_t s = window_decode(b, lut, lg);
+  cp_async_wait<0>();
+  return s;
+}
+
+__device__ __forceinline__ bool window_exact(const BitWindow& b) {
+  const int appended = (int)((b.wp0 - b.wp) >> 2);
+  const int consumed = b.loaded0 + 32 * appended - b.avail;
   return consumed == (int)b.unread;
 }
 
@@ -201,82 +323,277 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
   }
 }
 
-__global__ void __launch_bounds__(32) k_huf_decode_planar(const uint8_t* __restrict__ body, uint64_t body_len,
-                                                          const ItemDesc* __restrict__ items, uint64_t nitems,
-                                                          uint8_t* planes, uint64_t plane_stride, Ctrl* ctrl) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
+struct StreamSetup {
+  int lg;
+  uint32_t s_off, s_len;   // stream position inside the item (after the table description)
+  uint32_t out_off, count; // first symbol index and symbol count of this stream
+  const uint8_t* p;        // item payload after the table description
+};
+
+// Table description -> LUT (lane 0 of each item), then the jump table.  All 32 lanes call it;
+// returns false for lanes that have nothing to decode.
+__device__ __forceinline__ bool setup_item(DecodeSmem& S, const uint8_t* body, const ItemDesc& d, bool active, int slot,
+                                           int stream, Ctrl* ctrl, StreamSetup& st) {
   const int lane = threadIdx.x;
-  const int slot = lane >> 2;    // item within the warp
-  const int stream = lane & 3;   // bitstream within the item
-  const uint64_t item = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
-  const uint8_t* lo = body;
-  const uint8_t* hi = body + body_len;
-  const uint8_t* lo_aligned = reinterpret_cast<const uint8_t*>(((uintptr_t)lo + 3) & ~(uintptr_t)3);
-
-  ItemDesc d;
-  d.kind = kRaw;
-  d.src_off = 0;
-  d.src_len = 0;
-  d.dec_len = 0;
-  if (item < nitems) d = items[item];
-  const bool active = (d.kind == kHuf);
-  if (__ballot_sync(0xffffffffu, active) == 0) return;
-
-  // ---- table description -> weights -> LUT (one lane per item) ----
   int lg = 0, hsize = -1;
+  uint8_t* weights = &S.ring[0][0] + slot * 256;
   if (active && stream == 0) {
     int nsym = 0;
     FseDec& D = *reinterpret_cast<FseDec*>(&S.lut[slot][0]);
-    hsize = huf_read_weights(S.weights[slot], &nsym, &lg, body + d.src_off, d.src_len, D);
+    hsize = huf_read_weights(weights, &nsym, &lg, body + d.src_off, d.src_len, D);
     if (hsize >= 0 && lg > kDecLutLog) {
       atomicOr(&ctrl->error, kErrUnsupported);
       hsize = -1;
     } else if (hsize < 0) {
       atomicOr(&ctrl->error, kErrCorrupt);
     }
-    if (hsize >= 0) fill_lut(S.lut[slot], S.weights[slot], nsym, lg);
+    if (hsize >= 0) fill_lut(S.lut[slot], weights, nsym, lg);
   }
   __syncwarp();
   lg = __shfl_sync(0xffffffffu, lg, lane & ~3);
   hsize = __shfl_sync(0xffffffffu, hsize, lane & ~3);
-  if (!active || hsize < 0) return;
-
-  // ---- jump table (huf_decompress.c:283-290) ----
+  __syncwarp();  // the ring (aliased by weights) is free from here on
+  if (!active || hsize < 0) return false;
   const uint8_t* p = body + d.src_off + hsize;
   const uint32_t rest = d.src_len - (uint32_t)hsize;
   if (rest < 10) {
     atomicOr(&ctrl->error, kErrCorrupt);
-    return;
+    return false;
   }
   const uint32_t l0 = p[0] | (p[1] << 8), l1 = p[2] | (p[3] << 8), l2 = p[4] | (p[5] << 8);
   if (l0 + l1 + l2 + 6 > rest) {
     atomicOr(&ctrl->error, kErrCorrupt);
-    return;
+    return false;
   }
   const uint32_t l3 = rest - (l0 + l1 + l2 + 6);
   const uint32_t seg = (d.dec_len + 3) >> 2;
   if (3 * seg > d.dec_len || l0 == 0 || l1 == 0 || l2 == 0 || l3 == 0) {
     atomicOr(&ctrl->error, kErrCorrupt);
-    return;
+    return false;
   }
   uint32_t s_off = 6, s_len = l0;
   if (stream == 1) { s_off += l0; s_len = l1; }
   if (stream == 2) { s_off += l0 + l1; s_len = l2; }
   if (stream == 3) { s_off += l0 + l1 + l2; s_len = l3; }
-  const uint32_t out_off = (uint32_t)stream * seg;
-  const uint32_t count = (stream == 3) ? d.dec_len - 3 * seg : seg;
-
-  BitWindow b;
-  bool ok = window_init(b, p + s_off, s_len, lo, hi);
-  if (ok) ok = decode_stream_planar(b, S.lut[slot], lg, planes + item * plane_stride + out_off, count, lo_aligned);
-  if (!ok) atomicOr(&ctrl->error, kErrCorrupt);
+  st.lg = lg;
+  st.p = p;
+  st.s_off = s_off;
+  st.s_len = s_len;
+  st.out_off = (uint32_t)stream * seg;
+  st.count = (stream == 3) ? d.dec_len - 3 * seg : seg;
+  return true;
 }
 
 // ====================================================================================
-// Kernel 3: regroup byte planes into the element stream (+ un-rotate the sign bit).
-// Sources per (group, chunk): raw bytes inside the stream (unaligned), one RLE byte, or a
-// decoded plane in the workspace.  Each thread produces 16 output bytes per step.
+// Kernel 2a: general mode -- decode coded planes into workspace planes.
+// ====================================================================================
+__global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
+  const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
+  const uint64_t nitems = (uint64_t)cfg.G * cfg.K;
+  const uint64_t item = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
+  ItemDesc d;
+  d.kind = kRaw;
+  d.src_off = 0;
+  d.src_len = d.dec_len = 0;
+  bool active = false;
+  uint64_t c = 0;
+  int g = 0;
+  if (item < nitems) {
+    g = (int)(item / cfg.K);
+    c = item - (uint64_t)g * cfg.K;
+    if (cfg.mode[c] == kModeGeneral) {
+      d = cfg.items[item];
+      active = (d.kind == kHuf);
+    }
+  }
+  if (__ballot_sync(0xffffffffu, active) == 0) return;
+  StreamSetup st;
+  if (!setup_item(S, cfg.body, d, active, slot, stream, cfg.ctrl, st)) return;
+  uint8_t* dst = cfg.planes + ((uint64_t)cfg.slot[c] * cfg.G + g) * cfg.pstride + st.out_off;
+  BitWindow b;
+  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
+  if (ok) {
+    uint32_t done = 0;
+    if ((((uintptr_t)dst) & 15) == 0) {
+      const uint32_t n16 = st.count >> 4;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (uint32_t it = 0; it < n16; it++) {
+        uint32_t o[4];
+        decode16(b, S.lut[slot], st.lg, o);
+        d4[it] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      done = n16 << 4;
+    }
+    for (; done < st.count; done++) dst[done] = (uint8_t)decode1(b, S.lut[slot], st.lg);
+    ok = window_exact(b);
+  }
+  if (!ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+}
+
+// ====================================================================================
+// Kernel 2b: fused mode.  The lane that decodes 16 symbols of the coded plane also fetches
+// the 16 matching bytes of each other plane (raw bytes in the stream at any alignment, or
+// a replicated RLE block read with stride 0), interleaves, un-rotates and stores 16*G bytes
+// of elements.  The other planes are loaded as aligned 16-byte blocks one iteration ahead.
+// ====================================================================================
+struct SidePlane {
+  const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
+  uint32_t shift;    // byte offset (0..15) of that byte inside the block
+  uint32_t step;     // 1 for stream bytes, 0 for an RLE fill block
+  uint4 a, b;        // blocks k, k+1 (k+2 is in flight in `c`)
+  uint4 c;
+};
+
+__device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
+
+// 16 bytes starting `shift` bytes into the 32-byte pair (a, b).
+__device__ __forceinline__ void take16(const uint4& a, const uint4& b, uint32_t shift, uint32_t (&out)[4]) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const uint32_t bs = (shift & 3) * 8;
+  uint32_t t[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) t[i] = __funnelshift_r(w[i], w[i + 1], bs);
+  const bool s4 = shift & 4, s8 = shift & 8;
+  uint32_t u[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) u[i] = s8 ? t[i + 2] : t[i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = s4 ? u[i + 1] : u[i];
+}
+
+template <int G>
+__global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
+  const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
+  const uint64_t K = cfg.K;
+  const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
+  bool active = (c < K) && cfg.mode[c] == kModeFused;
+  if (__ballot_sync(0xffffffffu, active) == 0) return;
+
+  ItemDesc d;
+  d.kind = kRaw;
+  d.src_off = 0;
+  d.src_len = d.dec_len = 0;
+  int gh = 0;  // the coded group
+  if (active) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const ItemDesc t = cfg.items[(uint64_t)g * K + c];
+      if (t.kind == kHuf) {
+        d = t;
+        gh = g;
+      }
+    }
+  }
+  StreamSetup st;
+  if (!setup_item(S, cfg.body, d, active, slot, stream, cfg.ctrl, st)) return;
+
+  // ---- the other planes (indexed by group; the slot of the coded group stays unused) ----
+  SidePlane side[G];
+  const uint4* hi_block = reinterpret_cast<const uint4*>(((uintptr_t)(cfg.body + cfg.body_len) - 1) & ~(uintptr_t)15);
+  if (G > 1) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (g != gh) {
+        const uint64_t i = (uint64_t)g * K + c;
+        const ItemDesc t = cfg.items[i];
+        const uint8_t* p;
+        if (t.kind == kRle) {
+          p = cfg.fill + i * kFillBytes;
+          side[g].step = 0;
+        } else {
+          p = cfg.body + t.src_off + st.out_off;
+          side[g].step = 1;
+        }
+        side[g].shift = (uint32_t)((uintptr_t)p & 15);
+        side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)p & ~(uintptr_t)15);
+        side[g].a = ldg128(side[g].blk);
+        const uint4* nb = side[g].blk + side[g].step;
+        side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+      }
+    }
+  }
+
+  uint8_t* out_c = out + c * (uint64_t)cfg.chunk + (uint64_t)st.out_off * G;
+  const bool rot = (cfg.bits_mode == 1) && (G > 1);
+
+  BitWindow b;
+  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
+  if (ok) {
+    const uint32_t n16 = st.count >> 4;  // fused chunks have count % 16 == 0
+    for (uint32_t it = 0; it < n16; it++) {
+      // prefetch block k+2 of every side plane (used next iteration)
+      if (G > 1) {
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          if (g != gh) {
+            const uint4* nb = side[g].blk + 2 * side[g].step;
+            side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+          }
+        }
+      }
+      uint32_t dsym[4];
+      decode16(b, S.lut[slot], st.lg, dsym);
+      if (G == 1) {
+        *reinterpret_cast<uint4*>(out_c + 16 * it) = make_uint4(dsym[0], dsym[1], dsym[2], dsym[3]);
+      } else {
+        uint32_t pl[G][4];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          if (g == gh) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) pl[g][q] = dsym[q];
+          } else {
+            take16(side[g].a, side[g].b, side[g].shift, pl[g]);
+          }
+        }
+        uint32_t w[4 * G];
+        if (G == 2) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            w[2 * q] = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140);
+            w[2 * q + 1] = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint32_t t0 = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140), t1 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x5140);
+            const uint32_t t2 = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362), t3 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x7362);
+            w[4 * q] = __byte_perm(t0, t1, 0x5410);
+            w[4 * q + 1] = __byte_perm(t0, t1, 0x7632);
+            w[4 * q + 2] = __byte_perm(t2, t3, 0x5410);
+            w[4 * q + 3] = __byte_perm(t2, t3, 0x7632);
+          }
+        }
+        if (rot) {
+#pragma unroll
+          for (int q = 0; q < 4 * G; q++) w[q] = unrot_word<G>(w[q]);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out_c + (uint64_t)16 * G * it);
+#pragma unroll
+        for (int q = 0; q < G; q++) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          if (g != gh) {
+            side[g].a = side[g].b;
+            side[g].b = side[g].c;
+            side[g].blk += side[g].step;
+          }
+        }
+      }
+    }
+    ok = window_exact(b);
+  }
+  if (!ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+}
+
+// ====================================================================================
+// Kernel 3: regroup byte planes into the element stream (+ un-rotate the sign bit), for
+// chunks the fused kernel did not take.  Sources per (group, chunk): raw bytes inside the
+// stream (unaligned), one RLE byte, or a decoded plane in the workspace.
 // ====================================================================================
 struct PlaneSrc {
   const uint8_t* ptr;  // first plane byte (any alignment); nullptr => constant fill
@@ -284,7 +601,6 @@ struct PlaneSrc {
   uint32_t len;        // plane bytes
 };
 
-// n <= 16 consecutive bytes of a plane starting at byte index j (n multiple of 4).
 template <int NW>
 __device__ __forceinline__ void load_plane_words(const PlaneSrc& s, uint32_t j, uint32_t (&out)[NW]) {
   if (s.ptr == nullptr) {
@@ -311,41 +627,40 @@ constexpr int kMergeThreads = 256;
 constexpr uint32_t kMergeTile = kMergeThreads * 16 * 4;  // bytes of output per block step (16 KiB)
 
 template <int G>
-__global__ void __launch_bounds__(kMergeThreads) k_regroup(const uint8_t* __restrict__ body,
-                                                           const ItemDesc* __restrict__ items, uint64_t K,
-                                                           const uint8_t* __restrict__ planes, uint64_t plane_stride,
-                                                           uint32_t chunk, uint64_t orig, int bits_mode,
-                                                           uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(kMergeThreads) k_regroup(DecodeCfg cfg, uint8_t* __restrict__ out) {
   __shared__ PlaneSrc src[G];
+  const uint64_t K = cfg.K;
+  const uint32_t chunk = cfg.chunk;
   const uint32_t tiles_per_chunk = (chunk + kMergeTile - 1) / kMergeTile;
   const uint64_t ntiles = K * tiles_per_chunk;
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint64_t c = t / tiles_per_chunk;
+    if (cfg.mode[c] == kModeFused) continue;  // whole chunk already written by the fused kernel
     const uint32_t tile = (uint32_t)(t - c * tiles_per_chunk);
-    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(orig - c * (uint64_t)chunk) : chunk;
+    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)chunk) : chunk;
     const uint32_t o_begin = tile * kMergeTile;
     if (o_begin >= chunk_len) continue;
     __syncthreads();
     if (threadIdx.x < G) {
       const int g = threadIdx.x;
-      const ItemDesc d = items[(uint64_t)g * K + c];
+      const ItemDesc d = cfg.items[(uint64_t)g * K + c];
       PlaneSrc s;
       s.len = d.dec_len;
       s.fill = 0;
       if (d.kind == kRaw) {
-        s.ptr = body + d.src_off;
+        s.ptr = cfg.body + d.src_off;
       } else if (d.kind == kRle) {
         s.ptr = nullptr;
-        s.fill = 0x01010101u * (uint32_t)body[d.src_off];
+        s.fill = 0x01010101u * (uint32_t)cfg.body[d.src_off];
       } else {
-        s.ptr = planes + ((uint64_t)g * K + c) * plane_stride;
+        s.ptr = cfg.planes + ((uint64_t)cfg.slot[c] * G + g) * cfg.pstride;
       }
       src[g] = s;
     }
     __syncthreads();
     uint8_t* out_c = out + c * (uint64_t)chunk;
     const uint32_t o_end = min(chunk_len, o_begin + kMergeTile);
-    const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;  // words that get un-rotated
+    const uint32_t rot_words = (cfg.bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;  // words that get un-rotated
     for (uint32_t o = o_begin + threadIdx.x * 16; o < o_end; o += kMergeThreads * 16) {
       if (o + 16 <= o_end) {
         uint32_t r[4];
@@ -354,7 +669,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_regroup(const uint8_t* __rest
         } else if (G == 2) {
           uint32_t a[2], b2[2];
           load_plane_words<2>(src[0], o >> 1, a);
-          load_plane_words<2>(src[1], o >> 1, b2);
+          load_plane_words<2>(src[1 % G], o >> 1, b2);
           r[0] = __byte_perm(a[0], b2[0], 0x5140);
           r[1] = __byte_perm(a[0], b2[0], 0x7362);
           r[2] = __byte_perm(a[1], b2[1], 0x5140);
@@ -379,7 +694,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_regroup(const uint8_t* __rest
         *reinterpret_cast<uint4*>(out_c + o) = make_uint4(r[0], r[1], r[2], r[3]);
       } else {
         // ragged tail of the last chunk: byte by byte, whole words still get un-rotated
-        for (uint32_t q = o; q < o_end; q += 4) {
+        for (uint32_t q = o; q < min(o + 16, o_end); q += 4) {
           uint32_t w = 0;
           const uint32_t nb = min(4u, o_end - q);
           for (uint32_t i = 0; i < nb; i++) {

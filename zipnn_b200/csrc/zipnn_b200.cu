@@ -43,9 +43,9 @@ inline bool cuda_ok(cudaError_t e) {
 // ---- optional per-kernel timing (CUDA events on the launching stream) ----------------
 // Off by default.  bench.py turns it on to attribute the step time to kernels; the events
 // sit between launches on the same stream, so they do not change the schedule.
-enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKRegroup, kKEncodeStats, kKEncodeScan, kKEncodeWrite, kKSplit,
+enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKHufDecodePlanar, kKRegroup, kKEncodeStats, kKEncodeScan, kKEncodeWrite, kKSplit,
                 kKRegroupPlanar, kKCount };
-const char* const kKernelNames[kKCount] = {"k_decode_meta", "k_huf_decode", "k_regroup", "k_encode_stats",
+const char* const kKernelNames[kKCount] = {"k_decode_meta", "k_huf_decode_fused", "k_huf_decode_planar", "k_regroup", "k_encode_stats",
                                            "k_encode_scan", "k_encode_write", "k_split_planar", "k_regroup_planar"};
 struct TimedSpan {
   int id;
@@ -112,17 +112,24 @@ inline bool valid_layout(int num_buf, int bytes_mode, size_t chunk) {
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline uint64_t num_chunks(size_t n, size_t chunk) { return (n + chunk - 1) / chunk; }
 
-// ---- decompress workspace layout:  [Ctrl 256][ItemDesc G*K][planes G*K*pstride] ----
+// ---- decompress workspace layout ----
+//   [Ctrl 256][ItemDesc G*K][mode u8 K][slot u32 K][fill 64*G*K][planes slots*G*pstride]
+// `planes` is only used by chunks the fused kernel cannot take (several coded groups, or the
+// ragged last chunk); the default size provides kDefaultSlots of them, the "full" size K.
+constexpr uint64_t kDefaultSlots = 64;
 struct DecWs {
-  size_t items_off, planes_off, pstride, total;
+  size_t items_off, mode_off, slot_off, fill_off, planes_off, pstride, fixed;
 };
 inline DecWs dec_ws_layout(size_t orig, int G, size_t chunk) {
   DecWs L;
   const uint64_t K = num_chunks(orig, chunk);
   L.items_off = kCtrlBytes;
-  L.planes_off = round_up(L.items_off + sizeof(ItemDesc) * (size_t)G * K, 256);
-  L.pstride = round_up(chunk / (size_t)G, 16);
-  L.total = L.planes_off + (size_t)G * K * L.pstride + 256;
+  L.mode_off = round_up(L.items_off + sizeof(ItemDesc) * (size_t)G * K, 256);
+  L.slot_off = round_up(L.mode_off + K, 256);
+  L.fill_off = round_up(L.slot_off + 4 * K, 256);
+  L.planes_off = round_up(L.fill_off + (size_t)kFillBytes * G * K, 256);
+  L.pstride = round_up(chunk / (size_t)G, 16) + 16;
+  L.fixed = L.planes_off + 256;
   return L;
 }
 
@@ -141,6 +148,7 @@ int read_ctrl_error(void* d_ws, cudaStream_t st) {
   ZB_CUDA(cudaStreamSynchronize(st));
   if (err & kErrCorrupt) return ZIPNN_B200_E_CORRUPT;
   if (err & kErrUnsupported) return ZIPNN_B200_E_UNSUPPORTED;
+  if (err & kErrWorkspace) return ZIPNN_B200_E_CAPACITY;
   return ZIPNN_B200_OK;
 }
 
@@ -208,7 +216,16 @@ int zipnn_b200_compress_bound(size_t n, int num_buf, size_t chunk, size_t hdr_le
 
 int zipnn_b200_decompress_workspace_size(size_t orig, int num_buf, size_t chunk, size_t* out) {
   if (!out || chunk == 0 || !(num_buf == 1 || num_buf == 2 || num_buf == 4)) return ZIPNN_B200_E_ARG;
-  *out = dec_ws_layout(orig, num_buf, chunk).total;
+  const DecWs L = dec_ws_layout(orig, num_buf, chunk);
+  const uint64_t K = num_chunks(orig, chunk);
+  *out = L.fixed + (size_t)std::min<uint64_t>(K, kDefaultSlots) * num_buf * L.pstride;
+  return ZIPNN_B200_OK;
+}
+
+int zipnn_b200_decompress_workspace_size_full(size_t orig, int num_buf, size_t chunk, size_t* out) {
+  if (!out || chunk == 0 || !(num_buf == 1 || num_buf == 2 || num_buf == 4)) return ZIPNN_B200_E_ARG;
+  const DecWs L = dec_ws_layout(orig, num_buf, chunk);
+  *out = L.fixed + (size_t)num_chunks(orig, chunk) * num_buf * L.pstride;
   return ZIPNN_B200_OK;
 }
 
@@ -223,29 +240,51 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   const uint64_t K = num_chunks(orig, chunk);
   if (body_len < 9ull * G * K) return ZIPNN_B200_E_CORRUPT;
   const DecWs L = dec_ws_layout(orig, G, chunk);
-  if (ws_bytes < L.total) return ZIPNN_B200_E_CAPACITY;
+  if (ws_bytes < L.fixed) return ZIPNN_B200_E_CAPACITY;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   uint8_t* ws = (uint8_t*)d_ws;
-  Ctrl* ctrl = (Ctrl*)ws;
-  ItemDesc* items = (ItemDesc*)(ws + L.items_off);
-  uint8_t* planes = ws + L.planes_off;
-  const uint8_t* body = (const uint8_t*)d_body;
+  DecodeCfg cfg;
+  cfg.body = (const uint8_t*)d_body;
+  cfg.body_len = body_len;
+  cfg.G = G;
+  cfg.K = K;
+  cfg.chunk = (uint32_t)chunk;
+  cfg.orig = orig;
+  cfg.bits_mode = bits_mode;
+  cfg.ctrl = (Ctrl*)ws;
+  cfg.items = (ItemDesc*)(ws + L.items_off);
+  cfg.mode = ws + L.mode_off;
+  cfg.slot = (uint32_t*)(ws + L.slot_off);
+  cfg.fill = ws + L.fill_off;
+  cfg.planes = ws + L.planes_off;
+  cfg.pstride = L.pstride;
+  cfg.max_slots = (uint32_t)std::min<uint64_t>((ws_bytes - L.fixed) / ((size_t)G * L.pstride), K);
   const uint64_t nitems = (uint64_t)G * K;
 
-  ZB_CUDA(cudaMemsetAsync(ctrl, 0, kCtrlBytes, st));
+  ZB_CUDA(cudaMemsetAsync(cfg.ctrl, 0, kCtrlBytes, st));
   {
-    const int threads = 256;
-    const int blocks = (int)std::min<uint64_t>((nitems + threads - 1) / threads, 4096);
+    const int threads = 128;
+    const int blocks = (int)std::min<uint64_t>((K + threads - 1) / threads, 4096);
     ScopedTimer tm(kKDecodeMeta, st);
-    k_decode_meta<<<blocks, threads, 0, st>>>(body, body_len, G, K, (uint32_t)chunk, orig, ctrl, items);
+    k_decode_meta<<<blocks, threads, 0, st>>>(cfg);
     ZB_LAUNCHED();
+  }
+  {
+    const uint64_t warps = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
+    if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
+    ScopedTimer tm(kKHufDecode, st);
+    int rc = dispatch_G(G, [&](auto g) -> int {
+      k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, sizeof(DecodeSmem), st>>>(cfg, (uint8_t*)d_out);
+      ZB_LAUNCHED();
+      return ZIPNN_B200_OK;
+    });
+    if (rc) return rc;
   }
   {
     const uint64_t warps = (nitems + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
-    ScopedTimer tm(kKHufDecode, st);
-    k_huf_decode_planar<<<(unsigned)warps, 32, sizeof(DecodeSmem), st>>>(body, body_len, items, nitems, planes,
-                                                                         L.pstride, ctrl);
+    ScopedTimer tm(kKHufDecodePlanar, st);
+    k_huf_decode_planar<<<(unsigned)warps, 32, sizeof(DecodeSmem), st>>>(cfg);
     ZB_LAUNCHED();
   }
   {
@@ -254,8 +293,7 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     const int blocks = (int)std::min<uint64_t>(ntiles, (uint64_t)sm_count_cached() * 16);
     ScopedTimer tm(kKRegroup, st);
     int rc = dispatch_G(G, [&](auto g) -> int {
-      k_regroup<decltype(g)::value><<<blocks, kMergeThreads, 0, st>>>(body, items, K, planes, L.pstride, (uint32_t)chunk,
-                                                                      orig, bits_mode, (uint8_t*)d_out);
+      k_regroup<decltype(g)::value><<<blocks, kMergeThreads, 0, st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });

@@ -415,9 +415,14 @@ def _decompress_device(body: torch.Tensor, num_buf: int, bits_mode: int, bytes_m
         out = torch.empty(orig, dtype=torch.uint8, device=body.device)
         if orig == 0:
             return out
-        ws = torch.empty(_native.decompress_workspace_size(orig, num_buf, chunk), dtype=torch.uint8, device=body.device)
-        st = L.zipnn_b200_decompress(body.data_ptr(), body.numel(), num_buf, bits_mode, bytes_mode, chunk, orig,
-                                     out.data_ptr(), ws.data_ptr(), ws.numel(), _cuda_stream_handle(), 1)
+        st = _native.E_CAPACITY
+        for full in (False, True):   # the full workspace is only needed by unusual streams
+            ws = torch.empty(_native.decompress_workspace_size(orig, num_buf, chunk, full=full), dtype=torch.uint8,
+                             device=body.device)
+            st = L.zipnn_b200_decompress(body.data_ptr(), body.numel(), num_buf, bits_mode, bytes_mode, chunk, orig,
+                                         out.data_ptr(), ws.data_ptr(), ws.numel(), _cuda_stream_handle(), 1)
+            if st != _native.E_CAPACITY:
+                break
     if st == _native.E_CORRUPT:
         raise RuntimeError("Thread processing failed: corrupt ZipNN stream")  # reference: zipnn_core.c:1089
     _native.check(st)
