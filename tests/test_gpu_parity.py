@@ -188,6 +188,14 @@ def test_unaligned_views_and_noncontiguous_inputs():
     assert torch.equal(back.view(torch.int16), base.view(torch.int16))
 
 
+def _expect_corrupt(stream):
+    """Must be rejected as a corrupt stream -- not fail with a CUDA error that merely happens to
+    be a RuntimeError too -- and must leave the device usable."""
+    with pytest.raises(RuntimeError, match="corrupt"):
+        ZipNN(input_format="torch").decompress(stream)
+    torch.cuda.synchronize()
+
+
 def test_corrupt_streams_are_rejected():
     t = (torch.randn(200000) * 0.02).to(torch.bfloat16).cuda()
     s = ZipNN(input_format="torch").compress(t).clone()
@@ -197,18 +205,23 @@ def test_corrupt_streams_are_rejected():
         ZipNN(input_format="torch").decompress(bad)
     hdr_len = 32 + 1 + 4  # 1-D shape, 4-byte dim
     bad = s.clone()
-    bad[hdr_len + 1] = 7  # type byte of (group 1, chunk 0) out of range
-    with pytest.raises(RuntimeError):
-        ZipNN(input_format="torch").decompress(bad)
+    bad[hdr_len + 2] = 7  # type byte of (group 1, chunk 0) out of range
+    _expect_corrupt(bad)
     bad = s.clone()
     bad[-1] = 0  # last stream loses its end mark
-    with pytest.raises(RuntimeError):
-        ZipNN(input_format="torch").decompress(bad)
+    _expect_corrupt(bad)
     bad = s.clone()
     K = 2
-    bad[hdr_len + 2 * K + 8 * K + 3] ^= 0x40  # cumulative size of group 1 scrambled
-    with pytest.raises(RuntimeError):
+    bad[hdr_len + 2 * K + 8 * K + 3] ^= 0x40  # cumulative size of (group 1, chunk 0) scrambled
+    _expect_corrupt(bad)
+    bad = s.clone()
+    bad[hdr_len + 2 * K + 16 * K + 200000 + 3] ^= 0xFF  # inside the table description of the first coded block
+    try:
         ZipNN(input_format="torch").decompress(bad)
+    except RuntimeError as e:
+        assert "corrupt" in str(e)
+    torch.cuda.synchronize()
+    _expect_corrupt(s[: s.numel() - 1000].clone())  # truncated
     # random bit flips inside the Huffman payload: either a clean error or wrong data, never a crash
     rng = np.random.default_rng(1)
     for _ in range(20):
@@ -217,9 +230,11 @@ def test_corrupt_streams_are_rejected():
         bad[pos] ^= 1 << int(rng.integers(0, 8))
         try:
             ZipNN(input_format="torch").decompress(bad)
-        except RuntimeError:
-            pass
-    torch.cuda.synchronize()
+        except RuntimeError as e:
+            assert "corrupt" in str(e)
+        torch.cuda.synchronize()
+    good = ZipNN(input_format="torch").decompress(s)
+    assert torch.equal(good.view(torch.int16), t.view(torch.int16))
 
 
 def test_reference_stress_sizes_round_trip():

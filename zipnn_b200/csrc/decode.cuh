@@ -19,7 +19,7 @@
 
 namespace zb {
 
-enum : uint32_t { kModePlain = 0, kModeFused = 1, kModeGeneral = 2 };
+enum : uint32_t { kModePlain = 0, kModeFused = 1, kModeGeneral = 2, kModeSkip = 3 };
 constexpr uint32_t kFillBytes = 64;  // replicated RLE byte block per item (read with stride 0)
 
 struct DecodeCfg {
@@ -117,7 +117,7 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
     // 16-element boundaries: chunk_len a multiple of 64*G.  Anything else goes the general way.
     uint32_t m = kModePlain;
     if (bad_chunk) {
-      m = kModePlain;
+      m = kModeSkip;  // rejected: nothing may be read through its (untrusted) offsets
     } else if (nhuf == 1 && (chunk_len % (64u * (uint32_t)G)) == 0) {
       m = kModeFused;
     } else if (nhuf >= 1) {
@@ -125,11 +125,7 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
       const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
       if (s >= cfg.max_slots) {
         atomicOr(&cfg.ctrl->error, kErrWorkspace);
-        m = kModePlain;
-        for (int g = 0; g < G; g++) {  // neutralise: nothing will decode this chunk
-          cfg.items[(uint64_t)g * K + c].kind = kRaw;
-          cfg.items[(uint64_t)g * K + c].dec_len = 0;
-        }
+        m = kModeSkip;  // the caller retries with the full workspace
       } else {
         cfg.slot[c] = s;
       }
@@ -635,7 +631,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_regroup(DecodeCfg cfg, uint8_
   const uint64_t ntiles = K * tiles_per_chunk;
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint64_t c = t / tiles_per_chunk;
-    if (cfg.mode[c] == kModeFused) continue;  // whole chunk already written by the fused kernel
+    if (cfg.mode[c] == kModeFused || cfg.mode[c] == kModeSkip) continue;  // written by the fused kernel / rejected
     const uint32_t tile = (uint32_t)(t - c * tiles_per_chunk);
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)chunk) : chunk;
     const uint32_t o_begin = tile * kMergeTile;
