@@ -49,9 +49,18 @@ __device__ __forceinline__ uint32_t rot_byte_at(const uint8_t* __restrict__ in_c
 // =====================================================================================
 // pass A
 // =====================================================================================
+// Histogram replicas: every lane of a warp owns a column, so the 32 shared-memory atomics of
+// one warp instruction always hit 32 different banks (word index = row * R + lane % R, R = 32;
+// for four groups R = 16 to stay inside shared memory, which costs at most a 2-way conflict).
+// Two 16-bit counters share a word: a stream quarter holds at most 32768 symbols.
+template <int G>
+struct StatsCfg {
+  static constexpr int R = (G == 4) ? 16 : 32;
+};
+
 template <int G>
 struct StatsSmem {
-  uint32_t rep[G][8][128];   // 8 lane-keyed replicas, two 16-bit counters per word
+  uint32_t rep[G][128][StatsCfg<G>::R];
   uint16_t hist[G][4][256];  // per stream
   uint32_t total[G][256];
   uint8_t nb[G][256];
@@ -60,8 +69,8 @@ struct StatsSmem {
 };
 
 template <int G>
-__device__ __forceinline__ void hist_add(StatsSmem<G>& S, int g, int r, uint32_t b) {
-  atomicAdd(&S.rep[g][r][b >> 1], 1u << (16 * (b & 1)));
+__device__ __forceinline__ void hist_add(StatsSmem<G>& S, int g, int col, uint32_t b) {
+  atomicAdd(&S.rep[g][b >> 1][col], 1u << (16 * (b & 1)));
 }
 
 // One warp: everything the reference does per block after the histogram
@@ -181,26 +190,38 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_stats(const uint8_t* __r
                                                               uint32_t* sizes, EncSave* saves) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StatsSmem<G>& S = *reinterpret_cast<StatsSmem<G>*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, rep = lane & 7;
+  constexpr int R = StatsCfg<G>::R;
+  const int tid = threadIdx.x, lane = tid & 31, col = lane % R;
+  for (int i = tid; i < G * 128 * R; i += kEncThreads) (&S.rep[0][0][0])[i] = 0;
+  __syncthreads();
   for (uint64_t c = blockIdx.x; c < K; c += gridDim.x) {
     const uint8_t* in_c = in + c * (uint64_t)chunk;
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
     const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;
     const bool fast = (chunk_len % 64u) == 0;
     for (int q = 0; q < 4; q++) {
-      for (int i = tid; i < G * 8 * 128; i += kEncThreads) (&S.rep[0][0][0])[i] = 0;
-      __syncthreads();
       if (fast) {
         const uint32_t qbytes = chunk_len >> 2;  // bytes of input per stream quarter
         const uint4* src = reinterpret_cast<const uint4*>(in_c + (uint64_t)q * qbytes);
-        for (uint32_t u = tid; u < (qbytes >> 4); u += kEncThreads) {
-          const uint4 v = __ldg(src + u);
-          uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t nvec = qbytes >> 4;
+        for (uint32_t u0 = 0; u0 < nvec; u0 += 4 * kEncThreads) {
+          uint4 v[4];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            if (rot_words) w[i] = rot_word<G>(w[i]);
+          for (int k = 0; k < 4; k++) {  // four loads in flight per thread
+            const uint32_t u = u0 + k * kEncThreads + tid;
+            v[k] = (u < nvec) ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+          }
 #pragma unroll
-            for (int b = 0; b < 4; b++) hist_add<G>(S, (4 * i + b) % G, rep, (w[i] >> (8 * b)) & 0xFFu);
+          for (int k = 0; k < 4; k++) {
+            if (u0 + k * kEncThreads + tid < nvec) {
+              uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                if (rot_words) w[i] = rot_word<G>(w[i]);
+#pragma unroll
+                for (int b = 0; b < 4; b++) hist_add<G>(S, (4 * i + b) % G, col, (w[i] >> (8 * b)) & 0xFFu);
+              }
+            }
           }
         }
       } else {
@@ -209,16 +230,25 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_stats(const uint8_t* __r
           const uint32_t seg = (pl + 3) >> 2;
           const uint32_t j0 = min(pl, (uint32_t)q * seg), j1 = (q == 3) ? pl : min(pl, j0 + seg);
           for (uint32_t j = j0 + tid; j < j1; j += kEncThreads)
-            hist_add<G>(S, g, rep, rot_byte_at<G>(in_c, chunk_len, rot_words, j * G + g));
+            hist_add<G>(S, g, col, rot_byte_at<G>(in_c, chunk_len, rot_words, j * G + g));
         }
       }
       __syncthreads();
-      for (int i = tid; i < G * 256; i += kEncThreads) {
-        const int g = i >> 8, b = i & 255;
-        uint32_t t = 0;
-#pragma unroll
-        for (int r = 0; r < 8; r++) t += (S.rep[g][r][b >> 1] >> (16 * (b & 1))) & 0xFFFFu;
-        S.hist[g][q][b] = (uint16_t)t;
+      // fold the replicas of each bin pair (and clear them for the next quarter); the lane
+      // rotation keeps the 32 reads of a warp on 32 different banks
+      for (int i = tid; i < G * 128; i += kEncThreads) {
+        const int g = i >> 7, row = i & 127;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll 8
+        for (int r = 0; r < R; r++) {
+          const int rr = (r + lane) % R;
+          const uint32_t wv = S.rep[g][row][rr];
+          S.rep[g][row][rr] = 0;
+          lo += wv & 0xFFFFu;
+          hi += wv >> 16;
+        }
+        S.hist[g][q][2 * row] = (uint16_t)lo;
+        S.hist[g][q][2 * row + 1] = (uint16_t)hi;
       }
       __syncthreads();
     }

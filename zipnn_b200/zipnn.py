@@ -170,10 +170,13 @@ class ZipNN:
 
     # ------------------------------------------------------------------ compress
     def compress(self, data, compress_cpu_gpu="cpu", delta_second_data=None, lossy_compressed_type: str = None,
-                 lossy_compressed_factor: int = None):
+                 lossy_compressed_factor: int = None, out=None):
         """zipnn/zipnn.py:560-643.  Returns a `memoryview` for host inputs (as the reference
-        does) or a CUDA `uint8` tensor for CUDA inputs (or when compress_cpu_gpu == "gpu")."""
+        does) or a CUDA `uint8` tensor for CUDA inputs (or when compress_cpu_gpu == "gpu").
+        `out=` (extension): a CPU uint8 tensor, ideally pinned, to receive a host result --
+        lets a caller that codes many tensors reuse one staging buffer."""
         self._want_device_result = (compress_cpu_gpu == "gpu")
+        self._out = out
         if self.delta_compressed_type == "byte":
             if len(data) != len(delta_second_data):
                 raise ValueError("Length of delta file has to match the length of the original file.")
@@ -248,7 +251,8 @@ class ZipNN:
             return None
         if isinstance(flat_u8, torch.Tensor) and flat_u8.is_cuda:
             return _compress_device(flat_u8, python_header, num_buf, bit_reorder, byte_reorder, chunk, self.compression_threshold)
-        out = _compress_host(flat_u8, python_header, num_buf, bit_reorder, byte_reorder, chunk, self.compression_threshold)
+        out = _compress_host(flat_u8, python_header, num_buf, bit_reorder, byte_reorder, chunk, self.compression_threshold,
+                             out=getattr(self, "_out", None))
         if getattr(self, "_want_device_result", False):
             return torch.from_numpy(np.asarray(out)).cuda()
         return out
@@ -264,8 +268,10 @@ class ZipNN:
         return self._last_plan
 
     # ------------------------------------------------------------------ decompress
-    def decompress(self, data, decompress_cpu_gpu="cpu", delta_second_data=None):
-        """zipnn/zipnn.py:928-1005.  CUDA `uint8` tensor in -> CUDA result; host bytes in -> host result."""
+    def decompress(self, data, decompress_cpu_gpu="cpu", delta_second_data=None, out=None):
+        """zipnn/zipnn.py:928-1005.  CUDA `uint8` tensor in -> CUDA result; host bytes in -> host result.
+        `out=` (extension): CPU tensor (ideally pinned) that receives a host result."""
+        self._out = out
         if self.delta_compressed_type == "byte":
             if delta_second_data is None:
                 raise ValueError("delta_second_data is None or not set for delta copression")
@@ -344,7 +350,8 @@ class ZipNN:
         if isinstance(stream, torch.Tensor):
             out_u8 = _decompress_device(stream[after_header:], num_buf, self._bit_reorder, self._byte_reorder, chunk, n)
         else:
-            out_u8 = _decompress_host(stream[after_header:], num_buf, self._bit_reorder, self._byte_reorder, chunk, n)
+            out_u8 = _decompress_host(stream[after_header:], num_buf, self._bit_reorder, self._byte_reorder, chunk, n,
+                                      out=getattr(self, "_out", None))
 
         fmt = self.input_format
         if fmt == EnumFormat.BYTE.value:
@@ -433,34 +440,57 @@ def _pinned_empty(nbytes: int) -> torch.Tensor:
     return torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
 
 
-def _host_ptr(a):
-    return a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
+def _host_tensor(a) -> torch.Tensor:
+    """Flat uint8 CPU tensor over host bytes without copying (numpy arrays may be read-only)."""
+    if isinstance(a, torch.Tensor):
+        return a
+    if a.size == 0:
+        return torch.empty(0, dtype=torch.uint8)
+    if a.flags.writeable:
+        return torch.from_numpy(a)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return torch.from_numpy(a)   # only ever read from
+
+
+def _host_out(nbytes: int, out):
+    """Host destination for a result: the caller's buffer (`out=`), else fresh pinned memory
+    (torch's caching host allocator makes repeated calls cheap)."""
+    if out is None:
+        return _pinned_empty(nbytes)[:nbytes]
+    o = out.detach().reshape(-1)
+    o = o if o.dtype == torch.uint8 else o.view(torch.uint8)
+    if o.is_cuda or not o.is_contiguous() or o.numel() < nbytes:
+        raise ValueError("out= must be a contiguous CPU tensor with room for the result")
+    return o[:nbytes]
 
 
 def _compress_host(flat_u8, header: bytes, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int,
-                   threshold: float):
+                   threshold: float, out=None):
+    """Host bytes in, host bytes out: H2D copy, GPU codec, D2H copy of exactly the stream."""
     _native.require_cuda()
-    L = _native.lib()
-    n = flat_u8.numel() if isinstance(flat_u8, torch.Tensor) else flat_u8.size
-    bound = _native.compress_bound(n, num_buf, chunk, len(header))
-    out = _pinned_empty(bound)
-    out_len = C.c_size_t(0)
-    hdr = (C.c_char * len(header)).from_buffer_copy(header)
-    _native.check(L.zipnn_b200_compress_host(_host_ptr(flat_u8) if n else None, n, hdr, len(header), num_buf, bits_mode,
-                                             bytes_mode, chunk, threshold, out.data_ptr(), bound, C.byref(out_len)))
-    return memoryview(out.numpy()[: out_len.value])
+    src = _host_tensor(flat_u8)
+    dev_in = torch.empty(src.numel(), dtype=torch.uint8, device="cuda")
+    dev_in.copy_(src, non_blocking=True)
+    stream = _compress_device(dev_in, header, num_buf, bits_mode, bytes_mode, chunk, threshold)
+    host = _host_out(stream.numel(), out)
+    host.copy_(stream, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return memoryview(host.numpy())
 
 
-def _decompress_host(body: np.ndarray, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int, orig: int) -> torch.Tensor:
+def _decompress_host(body: np.ndarray, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int, orig: int, out=None) -> torch.Tensor:
     _native.require_cuda()
-    L = _native.lib()
-    out = _pinned_empty(orig)[:orig]
+    host = _host_out(orig, out)
     if orig == 0:
-        return out
-    body = np.ascontiguousarray(body)
-    st = L.zipnn_b200_decompress_host(body.ctypes.data, body.size, num_buf, bits_mode, bytes_mode, chunk, orig,
-                                      out.data_ptr())
-    if st == _native.E_CORRUPT:
-        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
-    _native.check(st)
-    return out
+        return host
+    src = _host_tensor(np.ascontiguousarray(body))
+    # 64 leading bytes keep the word-granular stream readers inside the allocation
+    dev = torch.empty(src.numel() + 64 + 16, dtype=torch.uint8, device="cuda")
+    dev_body = dev[64: 64 + src.numel()]
+    dev_body.copy_(src, non_blocking=True)
+    dec = _decompress_device(dev_body, num_buf, bits_mode, bytes_mode, chunk, orig)
+    host.copy_(dec, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host
