@@ -250,8 +250,34 @@ __device__ __forceinline__ void window_refill(BitWindow& b) {
   b.nxt = ring_word(b, b.wp);
 }
 
-__device__ __forceinline__ uint32_t window_decode(BitWindow& b, const uint16_t* lut, int lg) {
-  const uint32_t e = lut[(uint32_t)(b.w >> (64 - lg))];
+// ---- decode tables ------------------------------------------------------------------
+// Full table: 2^lg entries {symbol, length} (what huf_decompress.c:151-183 builds).
+struct LutFull {
+  const uint16_t* lut;
+  int lg;
+  __device__ __forceinline__ uint32_t get(uint64_t w) const { return lut[(uint32_t)(w >> (64 - lg))]; }
+};
+// Two-level table in an 11-bit index space (shorter table logs are replicated into it):
+// codes of <= 8 bits resolve in a 256-entry primary indexed by the top 8 bits; longer codes
+// sit at the bottom of the canonical order (index < x_long) and resolve in a tail table
+// indexed by all 11 bits.  Both are read every symbol and selected, so there is no branch.
+// 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
+constexpr int kTailEntries = 256;
+struct LutTwo {
+  const uint16_t* prim;
+  const uint16_t* tail;
+  uint32_t x_long;
+  __device__ __forceinline__ uint32_t get(uint64_t w) const {
+    const uint32_t idx = (uint32_t)(w >> 53);
+    const uint32_t e1 = prim[idx >> 3];
+    const uint32_t e2 = tail[idx & (kTailEntries - 1)];
+    return idx < x_long ? e2 : e1;
+  }
+};
+
+template <class LUT>
+__device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) {
+  const uint32_t e = lut.get(b.w);
   const int nb = (int)(e >> 8);
   b.w <<= nb;
   b.avail -= nb;
@@ -260,24 +286,26 @@ __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const uint16_t* 
 
 // 16 symbols -> 4 words (symbol j in byte j).  Ring maintenance for the NEXT iterations is
 // issued first so the copies overlap the decode.
-__device__ __forceinline__ void decode16(BitWindow& b, const uint16_t* lut, int lg, uint32_t (&o)[4]) {
+template <class LUT>
+__device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t (&o)[4]) {
   ring_top_up(b, 2);
   cp_async_commit();
   o[0] = o[1] = o[2] = o[3] = 0;
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
     window_refill(b);
-    o[j >> 2] |= window_decode(b, lut, lg) << (8 * (j & 3));
-    o[(j + 1) >> 2] |= window_decode(b, lut, lg) << (8 * ((j + 1) & 3));
+    o[j >> 2] |= window_decode(b, lut) << (8 * (j & 3));
+    o[(j + 1) >> 2] |= window_decode(b, lut) << (8 * ((j + 1) & 3));
   }
   cp_async_wait<1>();  // everything but the group just committed has landed
 }
 
-__device__ __forceinline__ uint32_t decode1(BitWindow& b, const uint16_t* lut, int lg) {
+template <class LUT>
+__device__ __forceinline__ uint32_t decode1(BitWindow& b, const LUT& lut) {
   ring_top_up(b, 1);
   cp_async_commit();
   window_refill(b);
-  const uint32_t s = window_decode(b, lut, lg);
+  const uint32_t s = window_decode(b, lut);
   cp_async_wait<0>();
   return s;
 }
@@ -317,6 +345,43 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
       for (uint32_t q = 0; q < len; q++) lut[u + q] = e;
     }
   }
+}
+
+// Two-level fill.  Returns the tail size (index bound of the long codes), or -1 when the
+// tail does not fit kTailEntries / the table log exceeds 11 (the caller demotes the chunk).
+__device__ __forceinline__ int fill_lut2(uint16_t* prim, uint16_t* tail, const uint8_t* weights, int nsym, int lg) {
+  if (lg > kDecLutLog) return -1;
+  uint32_t cnt[kHufLogMax + 2];
+#pragma unroll
+  for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
+  for (int n = 0; n < nsym; n++) cnt[weights[n]]++;
+  const int up = kDecLutLog - lg;  // replicate into the 11-bit index space
+  uint32_t start[kHufLogMax + 2];
+  uint32_t at = 0, x_long = 0;
+  start[0] = 0;
+  for (int w = 1; w <= lg; w++) {
+    start[w] = at;
+    const uint32_t span_all = (cnt[w] << (w - 1)) << up;
+    if (lg + 1 - w > 8) x_long = at + span_all;
+    at += span_all;
+  }
+  if (x_long > (uint32_t)kTailEntries) return -1;
+  for (int n = 0; n < nsym; n++) {
+    const int w = weights[n];
+    if (w == 0) continue;
+    const int len = lg + 1 - w;
+    const uint32_t span = 1u << (kDecLutLog - len);
+    const uint16_t e = (uint16_t)(n | (len << 8));
+    const uint32_t u = start[w];
+    start[w] = u + span;
+    if (len > 8) {
+      for (uint32_t q = 0; q < span; q++) tail[u + q] = e;
+    } else {
+      const uint32_t p0 = u >> 3, pn = span >> 3;
+      for (uint32_t q = 0; q < pn; q++) prim[p0 + q] = e;
+    }
+  }
+  return (int)x_long;
 }
 
 struct StreamSetup {
@@ -409,6 +474,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
   if (!setup_item(S, cfg.body, d, active, slot, stream, cfg.ctrl, st)) return;
   uint8_t* dst = cfg.planes + ((uint64_t)cfg.slot[c] * cfg.G + g) * cfg.pstride + st.out_off;
   BitWindow b;
+  const LutFull lut{S.lut[slot], st.lg};
   bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
   if (ok) {
     uint32_t done = 0;
@@ -417,12 +483,12 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
       uint4* d4 = reinterpret_cast<uint4*>(dst);
       for (uint32_t it = 0; it < n16; it++) {
         uint32_t o[4];
-        decode16(b, S.lut[slot], st.lg, o);
+        decode16(b, lut, o);
         d4[it] = make_uint4(o[0], o[1], o[2], o[3]);
       }
       done = n16 << 4;
     }
-    for (; done < st.count; done++) dst[done] = (uint8_t)decode1(b, S.lut[slot], st.lg);
+    for (; done < st.count; done++) dst[done] = (uint8_t)decode1(b, lut);
     ok = window_exact(b);
   }
   if (!ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
@@ -433,7 +499,15 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 // the 16 matching bytes of each other plane (raw bytes in the stream at any alignment, or
 // a replicated RLE block read with stride 0), interleaves, un-rotates and stores 16*G bytes
 // of elements.  The other planes are loaded as aligned 16-byte blocks one iteration ahead.
+// Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
 // ====================================================================================
+struct FusedSmem {
+  uint16_t prim[kDecItemsPerWarp][256];            // also scratch for the table parse
+  uint16_t tail[kDecItemsPerWarp][kTailEntries];
+  __align__(16) uint8_t ring[32][kRingBytes];      // weights[8][256] alias it during the parse
+};
+static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in one primary table");
+
 struct SidePlane {
   const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
   uint32_t shift;    // byte offset (0..15) of that byte inside the block
@@ -459,10 +533,19 @@ __device__ __forceinline__ void take16(const uint4& a, const uint4& b, uint32_t 
   for (int i = 0; i < 4; i++) out[i] = s4 ? u[i + 1] : u[i];
 }
 
+// Un-rotate at plane level: the two top byte planes hold [sign|mant7] (lo) and [exponent] (hi)
+// of every element; the element's real top bytes are hi' = sign|exp>>1, lo' = exp<<7|mant7.
+// 4 ops per 4 elements instead of 5 per 32-bit word after interleaving.
+__device__ __forceinline__ void unrotate_planes(uint32_t& lo, uint32_t& hi) {
+  const uint32_t sm = lo, e = hi;
+  hi = (sm & 0x80808080u) | ((e >> 1) & 0x7F7F7F7Fu);
+  lo = ((e << 7) & 0x80808080u) | (sm & 0x7F7F7F7Fu);
+}
+
 template <int G>
 __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
+  FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t K = cfg.K;
   const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
@@ -484,8 +567,63 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       }
     }
   }
-  StreamSetup st;
-  if (!setup_item(S, cfg.body, d, active, slot, stream, cfg.ctrl, st)) return;
+
+  // ---- table description -> two-level table (lane 0 of each chunk) ----
+  int lg = 0, hsize = -1, x_long = 0;
+  {
+    uint8_t* weights = &S.ring[0][0] + slot * 256;
+    if (active && stream == 0) {
+      int nsym = 0;
+      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.prim[slot][0]);
+      hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
+      if (hsize >= 0) {
+        x_long = fill_lut2(S.prim[slot], S.tail[slot], weights, nsym, lg);
+        if (x_long < 0) hsize = -1;
+      }
+      if (hsize < 0) {
+        // Not an error yet: a table that needs the big scratch, a long tail or log 12, or a
+        // corrupt one.  Hand the chunk to the general kernels, which decide.
+        const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
+        if (s >= cfg.max_slots) {
+          atomicOr(&cfg.ctrl->error, kErrWorkspace);
+          cfg.mode[c] = (uint8_t)kModeSkip;
+        } else {
+          cfg.slot[c] = s;
+          cfg.mode[c] = (uint8_t)kModeGeneral;
+        }
+      }
+    }
+    __syncwarp();
+    lg = __shfl_sync(0xffffffffu, lg, lane & ~3);
+    hsize = __shfl_sync(0xffffffffu, hsize, lane & ~3);
+    x_long = __shfl_sync(0xffffffffu, x_long, lane & ~3);
+    __syncwarp();  // the ring (aliased by weights) is free from here on
+  }
+  if (!active || hsize < 0) return;
+
+  // ---- jump table (huf_decompress.c:283-290) ----
+  const uint8_t* p = cfg.body + d.src_off + hsize;
+  const uint32_t rest = d.src_len - (uint32_t)hsize;
+  bool ok = rest >= 10;
+  uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+  if (ok) {
+    l0 = p[0] | (p[1] << 8);
+    l1 = p[2] | (p[3] << 8);
+    l2 = p[4] | (p[5] << 8);
+    ok = l0 + l1 + l2 + 6 <= rest;
+    l3 = rest - (l0 + l1 + l2 + 6);
+    ok = ok && l0 && l1 && l2 && l3;
+  }
+  if (!ok) {
+    atomicOr(&cfg.ctrl->error, kErrCorrupt);
+    return;
+  }
+  const uint32_t seg = d.dec_len >> 2;  // fused chunks: dec_len % 64 == 0
+  uint32_t s_off = 6, s_len = l0;
+  if (stream == 1) { s_off += l0; s_len = l1; }
+  if (stream == 2) { s_off += l0 + l1; s_len = l2; }
+  if (stream == 3) { s_off += l0 + l1 + l2; s_len = l3; }
+  const uint32_t out_off = (uint32_t)stream * seg;
 
   // ---- the other planes (indexed by group; the slot of the coded group stays unused) ----
   SidePlane side[G];
@@ -496,16 +634,16 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       if (g != gh) {
         const uint64_t i = (uint64_t)g * K + c;
         const ItemDesc t = cfg.items[i];
-        const uint8_t* p;
+        const uint8_t* q;
         if (t.kind == kRle) {
-          p = cfg.fill + i * kFillBytes;
+          q = cfg.fill + i * kFillBytes;
           side[g].step = 0;
         } else {
-          p = cfg.body + t.src_off + st.out_off;
+          q = cfg.body + t.src_off + out_off;
           side[g].step = 1;
         }
-        side[g].shift = (uint32_t)((uintptr_t)p & 15);
-        side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)p & ~(uintptr_t)15);
+        side[g].shift = (uint32_t)((uintptr_t)q & 15);
+        side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
         side[g].a = ldg128(side[g].blk);
         const uint4* nb = side[g].blk + side[g].step;
         side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
@@ -513,13 +651,14 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     }
   }
 
-  uint8_t* out_c = out + c * (uint64_t)cfg.chunk + (uint64_t)st.out_off * G;
+  uint8_t* out_c = out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G;
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
+  const LutTwo lut{S.prim[slot], S.tail[slot], (uint32_t)x_long};
 
   BitWindow b;
-  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
+  ok = window_init(b, p + s_off, s_len, cfg.body, S.ring[lane]);
   if (ok) {
-    const uint32_t n16 = st.count >> 4;  // fused chunks have count % 16 == 0
+    const uint32_t n16 = seg >> 4;
     for (uint32_t it = 0; it < n16; it++) {
       // prefetch block k+2 of every side plane (used next iteration)
       if (G > 1) {
@@ -532,7 +671,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
         }
       }
       uint32_t dsym[4];
-      decode16(b, S.lut[slot], st.lg, dsym);
+      decode16(b, lut, dsym);
       if (G == 1) {
         *reinterpret_cast<uint4*>(out_c + 16 * it) = make_uint4(dsym[0], dsym[1], dsym[2], dsym[3]);
       } else {
@@ -545,6 +684,10 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
           } else {
             take16(side[g].a, side[g].b, side[g].shift, pl[g]);
           }
+        }
+        if (rot) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) unrotate_planes(pl[G - 2][q], pl[G - 1][q]);
         }
         uint32_t w[4 * G];
         if (G == 2) {
@@ -563,10 +706,6 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
             w[4 * q + 2] = __byte_perm(t2, t3, 0x5410);
             w[4 * q + 3] = __byte_perm(t2, t3, 0x7632);
           }
-        }
-        if (rot) {
-#pragma unroll
-          for (int q = 0; q < 4 * G; q++) w[q] = unrot_word<G>(w[q]);
         }
         uint4* dst = reinterpret_cast<uint4*>(out_c + (uint64_t)16 * G * it);
 #pragma unroll

@@ -526,13 +526,20 @@ ZB_HD inline int huf_write_table(TreeScratch& T, const uint8_t* nb, int max_sym,
 // ---------------------------------------------------------------------------------
 // Decoder: table description -> weights.
 // ---------------------------------------------------------------------------------
-struct FseDec {
-  int16_t norm[256];
-  uint16_t next[256];
+// NSYM = how many distinct weight values the tANS header may declare.  The format allows 256;
+// every header the reference encoder writes declares at most 13 (weights 0..12), so the fused
+// decode kernel uses a 16-symbol scratch and hands anything larger to the general kernel.
+template <int NSYM>
+struct FseDecT {
+  int16_t norm[NSYM];
+  uint16_t next[NSYM];
   uint16_t new_state[64];
   uint8_t sym[64];
   uint8_t nb[64];
+  static constexpr int kSymbols = NSYM;
 };
+using FseDec = FseDecT<256>;
+using FseDecSmall = FseDecT<16>;
 
 // Forward LSB-first peek of n <= 16 bits at bit offset pos; zeros past the end.
 ZB_HD inline uint32_t peek_fwd(const uint8_t* src, uint32_t size, uint32_t pos, int n) {
@@ -610,7 +617,8 @@ ZB_HD inline int fse_read_ncount(int16_t* norm, int* max_sym_io, int* lg_out, co
   return used;
 }
 
-ZB_HD inline int fse_build_dec(FseDec& D, int max_sym, int lg) {
+template <class DEC>
+ZB_HD inline int fse_build_dec(DEC& D, int max_sym, int lg) {
   const uint32_t size = 1u << lg, mask = size - 1;
   const uint32_t step = (size >> 1) + (size >> 3) + 3;
   uint32_t high = size - 1;
@@ -675,8 +683,9 @@ struct BackBits {
 
 // Two interleaved tANS states; the stream ends when an update reads below bit 0.
 // Returns the number of symbols written to dst (<= cap), or -1.
-ZB_HD inline int fse_unpack(uint8_t* dst, int cap, const uint8_t* src, uint32_t size, int max_log, FseDec& D) {
-  int max_sym = 255, lg = 0;
+template <class DEC>
+ZB_HD inline int fse_unpack(uint8_t* dst, int cap, const uint8_t* src, uint32_t size, int max_log, DEC& D) {
+  int max_sym = DEC::kSymbols - 1, lg = 0;
   int h = fse_read_ncount(D.norm, &max_sym, &lg, src, size);
   if (h < 0) return -1;
   if (lg > max_log) return -1;
@@ -706,8 +715,9 @@ ZB_HD inline int fse_unpack(uint8_t* dst, int cap, const uint8_t* src, uint32_t 
 }
 
 // Table description -> weights[0..nsym).  Returns header size in bytes, or -1.
+template <class DEC>
 ZB_HD inline int huf_read_weights(uint8_t* weights /*256*/, int* nsym, int* lg_out, const uint8_t* src, uint32_t size,
-                                  FseDec& D) {
+                                  DEC& D) {
   if (size == 0) return -1;
   uint32_t isize = src[0];
   int osize;

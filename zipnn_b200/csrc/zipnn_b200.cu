@@ -274,7 +274,7 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
     ScopedTimer tm(kKHufDecode, st);
     int rc = dispatch_G(G, [&](auto g) -> int {
-      k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, sizeof(DecodeSmem), st>>>(cfg, (uint8_t*)d_out);
+      k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, sizeof(FusedSmem), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });
