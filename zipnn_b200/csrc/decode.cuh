@@ -62,7 +62,7 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
   }
   for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < K; c += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)cfg.chunk) : cfg.chunk;
-    int nhuf = 0;
+    int nhuf = 0, last_huf = -1;
     bool bad_chunk = false;
     for (int g = 0; g < G; g++) {
       const uint64_t i = (uint64_t)g * K + c;
@@ -104,7 +104,10 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
         d.dec_len = 0;
         bad_chunk = true;
       }
-      if (d.kind == kHuf) nhuf++;
+      if (d.kind == kHuf) {
+        nhuf++;
+        last_huf = g;
+      }
       if (d.kind == kRle) {
         const uint32_t v = 0x01010101u * (uint32_t)cfg.body[d.src_off];
         uint4* f = reinterpret_cast<uint4*>(cfg.fill + i * kFillBytes);
@@ -113,12 +116,13 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
       }
       cfg.items[i] = d;
     }
-    // The fused kernel wants whole, equally long planes whose quarter streams start on
+    // The fused kernel wants the one coded plane to be the top byte plane (the exponent side: what
+    // float tensors produce), and whole, equally long planes whose quarter streams start on
     // 16-element boundaries: chunk_len a multiple of 64*G.  Anything else goes the general way.
     uint32_t m = kModePlain;
     if (bad_chunk) {
       m = kModeSkip;  // rejected: nothing may be read through its (untrusted) offsets
-    } else if (nhuf == 1 && (chunk_len % (64u * (uint32_t)G)) == 0) {
+    } else if (nhuf == 1 && last_huf == G - 1 && (chunk_len % (64u * (uint32_t)G)) == 0) {
       m = kModeFused;
     } else if (nhuf >= 1) {
       m = kModeGeneral;
@@ -171,22 +175,23 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// Bit window, CPU style (bitstream.h:272-443) on top of the ring: a 64-bit container holding
+// bytes [p, p+8) of the stream and a count `c` of bits already consumed from its top.  A symbol
+// costs: peek = (container << c) >> 53, consume = c += length.  Every 4 symbols (4 x 11 bits
+// + 7 <= 64 - 11) the container is re-read at byte granularity: p -= c >> 3, c &= 7.  No branch.
 struct BitWindow {
-  uint64_t w;            // unread bits, left aligned
-  int avail;             // valid bits in w
-  uint32_t nxt;          // the word at `wp` (next to append)
-  uint32_t wp;           // byte offset (from gbase) of the next word to append; moves down
+  uint64_t cont;         // bytes [p, p+8) of the stream, little endian
+  uint32_t c;            // bits consumed from the top of `cont`
+  uint32_t p;            // byte offset (from gbase) of the container's lowest byte; moves down
   uint32_t fetch;        // byte offset (from gbase) of the lowest 16-byte block already requested
-  uint32_t wp0;          // wp right after init (for the exact-consumption check)
-  int loaded0;           // bits in the window right after init
-  uint32_t unread;       // bits between stream start and the end mark
+  uint32_t start_bit;    // bit offset (from gbase) of the first stream bit (exact-consumption check)
   const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
   uint32_t floor_off;    // do not request blocks below this offset (start of the stream buffer)
-  uint8_t* ring;
+  const uint8_t* ring;
 };
 
-__device__ __forceinline__ uint32_t ring_word(const BitWindow& b, uint32_t off) {
-  return *reinterpret_cast<const uint32_t*>(b.ring + (off & (kRingBytes - 1)));
+__device__ __forceinline__ uint32_t ring_word(const uint8_t* ring, uint32_t off) {
+  return *reinterpret_cast<const uint32_t*>(ring + (off & (kRingBytes - 4)));
 }
 
 // Request every 16-byte block that fits in the ring below what is still needed (<= `maxn`).
@@ -194,60 +199,55 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
 #pragma unroll 2
   for (int i = 0; i < maxn; i++) {
     const uint32_t f = b.fetch - 16;
-    // block [f, f+16) may overwrite ring bytes only if they are above everything still needed
-    // (the word at wp and the one above it): f + ring > wp + 8
-    if (b.fetch >= 16 + b.floor_off && f + kRingBytes > b.wp + 8) {
-      cp_async16(b.ring + (f & (kRingBytes - 1)), b.gbase + f);
+    // block [f, f+16) replaces ring bytes [f+128, f+144): allowed once they lie above the
+    // aligned words a reload of the container can still touch, (p & ~3) + 12
+    if (b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.p + 12) {
+      cp_async16(const_cast<uint8_t*>(b.ring) + (f & (kRingBytes - 1)), b.gbase + f);
       b.fetch = f;
     }
   }
 }
 
-// s points at the stream (len bytes); lo/hi bound the buffer that may be read.
+// Container := bytes [p, p+8) from the ring (three aligned words, funnel-shifted).
+__device__ __forceinline__ void window_load(BitWindow& b) {
+  const uint32_t a = b.p & ~3u;
+  const uint32_t w0 = ring_word(b.ring, a), w1 = ring_word(b.ring, a + 4), w2 = ring_word(b.ring, a + 8);
+  const uint32_t sh = (b.p & 3u) * 8;
+  const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+  b.cont = ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void window_reload(BitWindow& b) {
+  b.p -= b.c >> 3;
+  b.c &= 7u;
+  window_load(b);
+}
+
+// s points at the stream (len bytes); `lo` is the first readable byte of the buffer.
 __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo, uint8_t* ring) {
   const uint8_t lastb = s[len - 1];
   if (lastb == 0) return false;
   b.ring = ring;
-  b.gbase = reinterpret_cast<const uint8_t*>((uintptr_t)(s) & ~(uintptr_t)(kRingBytes - 1));
-  if (b.gbase < lo) {
-    // keep offsets non-negative relative to a base that is still 128-aligned
-    b.floor_off = (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15);
-  } else {
-    b.floor_off = 0;
-    // never read more than one ring below the item: those bytes are not needed
-  }
+  b.gbase = reinterpret_cast<const uint8_t*>(((uintptr_t)s & ~(uintptr_t)(kRingBytes - 1)) - kRingBytes);
+  // (one ring below the stream start keeps every offset the decoder forms non-negative)
+  b.floor_off = (b.gbase < lo) ? (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15) : 0u;
   const uint32_t s_off = (uint32_t)((uintptr_t)s - (uintptr_t)b.gbase);
   const uint32_t mark = 8u * (s_off + len - 1) + (uint32_t)hb32(lastb);  // bit offset of the end mark
-  b.unread = mark - 8u * s_off;
-  if (b.unread == 0) return false;
-  const uint32_t top_word = ((mark - 1) >> 3) & ~3u;       // offset of the word holding the top unread bit
-  const int k = (int)(mark - 8u * top_word);                // 1..32 unread bits in it
-  b.fetch = (top_word & ~15u) + 16;
-  b.wp = top_word;
+  b.start_bit = 8u * s_off;
+  if (mark == b.start_bit) return false;
+  const uint32_t top_byte = (mark - 1) >> 3;
+  b.p = top_byte - 7;
+  b.c = 8u * (top_byte + 1) - mark;  // 0..7 bits above the first unread bit
+  b.fetch = (top_byte & ~15u) + 16;
   ring_top_up(b, (int)(kRingBytes / 16));
   cp_async_commit();
   cp_async_wait<0>();
-  const uint32_t topw = ring_word(b, top_word);
-  const uint32_t low1 = (top_word >= 4) ? ring_word(b, top_word - 4) : 0u;
-  b.w = ((uint64_t)(topw << (32 - k)) << 32) | ((uint64_t)low1 << (32 - k));
-  b.avail = k + 32;
-  b.loaded0 = k + 32;
-  b.wp = top_word - 8;
-  b.wp0 = b.wp;
-  b.nxt = ring_word(b, b.wp);
+  window_load(b);
   return true;
 }
 
-// Branch-free: append `nxt` if the window has room for a whole word, then re-read the
-// word at (the possibly moved) wp.  Call at least every 2 symbols (2 x 11 bits <= 32).
-__device__ __forceinline__ void window_refill(BitWindow& b) {
-  const bool need = b.avail <= 32;
-  const uint32_t v = need ? b.nxt : 0u;
-  const int sh = need ? (32 - b.avail) : 0;
-  b.w |= (uint64_t)v << sh;
-  b.avail += need ? 32 : 0;
-  b.wp -= need ? 4u : 0u;
-  b.nxt = ring_word(b, b.wp);
+__device__ __forceinline__ bool window_exact(const BitWindow& b) {
+  return 8u * (b.p + 8) - b.c == b.start_bit;  // every bit down to the stream start consumed, none below
 }
 
 // ---- decode tables ------------------------------------------------------------------
@@ -255,33 +255,31 @@ __device__ __forceinline__ void window_refill(BitWindow& b) {
 struct LutFull {
   const uint16_t* lut;
   int lg;
-  __device__ __forceinline__ uint32_t get(uint64_t w) const { return lut[(uint32_t)(w >> (64 - lg))]; }
+  __device__ __forceinline__ uint32_t get(uint32_t top32) const { return lut[top32 >> (32 - lg)]; }
 };
 // Two-level table in an 11-bit index space (shorter table logs are replicated into it):
 // codes of <= 8 bits resolve in a 256-entry primary indexed by the top 8 bits; longer codes
 // sit at the bottom of the canonical order (index < x_long) and resolve in a tail table
-// indexed by all 11 bits.  Both are read every symbol and selected, so there is no branch.
+// indexed by all 11 bits (read only by the lanes that need it).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
 constexpr int kTailEntries = 256;
 struct LutTwo {
-  const uint16_t* prim;
-  const uint16_t* tail;
+  const uint16_t* tab;   // [0,256): primary, [256, 512): tail
   uint32_t x_long;
-  __device__ __forceinline__ uint32_t get(uint64_t w) const {
-    const uint32_t idx = (uint32_t)(w >> 53);
-    const uint32_t e1 = prim[idx >> 3];
-    const uint32_t e2 = tail[idx & (kTailEntries - 1)];
-    return idx < x_long ? e2 : e1;
+  __device__ __forceinline__ uint32_t get(uint32_t top32) const {
+    const uint32_t idx = top32 >> 21;
+    uint32_t e = tab[top32 >> 24];
+    if (idx < x_long) e = tab[256 + idx];
+    return e;
   }
 };
 
 template <class LUT>
 __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) {
-  const uint32_t e = lut.get(b.w);
-  const int nb = (int)(e >> 8);
-  b.w <<= nb;
-  b.avail -= nb;
-  return e & 0xFFu;
+  const uint32_t top32 = (uint32_t)((b.cont << b.c) >> 32);
+  const uint32_t e = lut.get(top32);
+  b.c += e >> 8;
+  return e;  // symbol in byte 0, length in byte 1
 }
 
 // 16 symbols -> 4 words (symbol j in byte j).  Ring maintenance for the NEXT iterations is
@@ -290,12 +288,12 @@ template <class LUT>
 __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t (&o)[4]) {
   ring_top_up(b, 2);
   cp_async_commit();
-  o[0] = o[1] = o[2] = o[3] = 0;
 #pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    window_refill(b);
-    o[j >> 2] |= window_decode(b, lut) << (8 * (j & 3));
-    o[(j + 1) >> 2] |= window_decode(b, lut) << (8 * ((j + 1) & 3));
+  for (int q = 0; q < 4; q++) {
+    window_reload(b);
+    const uint32_t e0 = window_decode(b, lut), e1 = window_decode(b, lut);
+    const uint32_t e2 = window_decode(b, lut), e3 = window_decode(b, lut);
+    o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
   }
   cp_async_wait<1>();  // everything but the group just committed has landed
 }
@@ -304,16 +302,10 @@ template <class LUT>
 __device__ __forceinline__ uint32_t decode1(BitWindow& b, const LUT& lut) {
   ring_top_up(b, 1);
   cp_async_commit();
-  window_refill(b);
-  const uint32_t s = window_decode(b, lut);
+  window_reload(b);
+  const uint32_t s = window_decode(b, lut) & 0xFFu;
   cp_async_wait<0>();
   return s;
-}
-
-__device__ __forceinline__ bool window_exact(const BitWindow& b) {
-  const int appended = (int)((b.wp0 - b.wp) >> 2);
-  const int consumed = b.loaded0 + 32 * appended - b.avail;
-  return consumed == (int)b.unread;
 }
 
 // Serial single-symbol table fill, one lane per item (huf_decompress.c:151-183): weights
@@ -349,7 +341,9 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
 
 // Two-level fill.  Returns the tail size (index bound of the long codes), or -1 when the
 // tail does not fit kTailEntries / the table log exceeds 11 (the caller demotes the chunk).
-__device__ __forceinline__ int fill_lut2(uint16_t* prim, uint16_t* tail, const uint8_t* weights, int nsym, int lg) {
+__device__ __forceinline__ int fill_lut2(uint16_t* tab, const uint8_t* weights, int nsym, int lg) {
+  uint16_t* prim = tab;
+  uint16_t* tail = tab + 256;
   if (lg > kDecLutLog) return -1;
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
@@ -502,11 +496,10 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 // Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
 // ====================================================================================
 struct FusedSmem {
-  uint16_t prim[kDecItemsPerWarp][256];            // also scratch for the table parse
-  uint16_t tail[kDecItemsPerWarp][kTailEntries];
+  uint16_t tab[kDecItemsPerWarp][512];             // primary + tail; also scratch for the table parse
   __align__(16) uint8_t ring[32][kRingBytes];      // weights[8][256] alias it during the parse
 };
-static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in one primary table");
+static_assert(sizeof(FseDecSmall) <= 1024, "small tANS scratch must fit in one table slot");
 
 struct SidePlane {
   const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
@@ -542,6 +535,61 @@ __device__ __forceinline__ void unrotate_planes(uint32_t& lo, uint32_t& hi) {
   lo = ((e << 7) & 0x80808080u) | (sm & 0x7F7F7F7Fu);
 }
 
+// One iteration: 16 symbols of the coded (top) plane + the matching bytes of the G-1 other
+// planes -> 16*G bytes of elements.  kGuard = clamp the look-ahead block loads to the end of
+// the stream buffer (only the last iterations of a stream can reach past it).
+template <int G, bool kGuard>
+__device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
+                                                const uint4* hi_block, bool rot, uint8_t* dst_bytes) {
+  if (G > 1) {
+#pragma unroll
+    for (int g = 0; g < G - 1; g++) {  // block k+2 of every side plane, used next iteration
+      const uint4* nb = side[g].blk + 2 * side[g].step;
+      if (kGuard && nb > hi_block) nb = hi_block;
+      side[g].c = ldg128(nb);
+    }
+  }
+  uint32_t pl[G][4];
+  decode16(b, lut, pl[G - 1]);
+  if (G == 1) {
+    *reinterpret_cast<uint4*>(dst_bytes) = make_uint4(pl[0][0], pl[0][1], pl[0][2], pl[0][3]);
+    return;
+  }
+#pragma unroll
+  for (int g = 0; g < G - 1; g++) take16(side[g].a, side[g].b, side[g].shift, pl[g]);
+  if (rot) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) unrotate_planes(pl[(G - 2) % G][q], pl[G - 1][q]);
+  }
+  uint32_t w[4 * G];
+  if (G == 2) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      w[2 * q] = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140);
+      w[2 * q + 1] = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint32_t t0 = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140), t1 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x5140);
+      const uint32_t t2 = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362), t3 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x7362);
+      w[4 * q] = __byte_perm(t0, t1, 0x5410);
+      w[4 * q + 1] = __byte_perm(t0, t1, 0x7632);
+      w[4 * q + 2] = __byte_perm(t2, t3, 0x5410);
+      w[4 * q + 3] = __byte_perm(t2, t3, 0x7632);
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(dst_bytes);
+#pragma unroll
+  for (int q = 0; q < G; q++) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+#pragma unroll
+  for (int g = 0; g < G - 1; g++) {
+    side[g].a = side[g].b;
+    side[g].b = side[g].c;
+    side[g].blk += side[g].step;
+  }
+}
+
 template <int G>
 __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -549,24 +597,14 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t K = cfg.K;
   const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
-  bool active = (c < K) && cfg.mode[c] == kModeFused;
+  const bool active = (c < K) && cfg.mode[c] == kModeFused;
   if (__ballot_sync(0xffffffffu, active) == 0) return;
 
-  ItemDesc d;
+  ItemDesc d;  // the coded plane: always group G-1 in fused mode
   d.kind = kRaw;
   d.src_off = 0;
   d.src_len = d.dec_len = 0;
-  int gh = 0;  // the coded group
-  if (active) {
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      const ItemDesc t = cfg.items[(uint64_t)g * K + c];
-      if (t.kind == kHuf) {
-        d = t;
-        gh = g;
-      }
-    }
-  }
+  if (active) d = cfg.items[(uint64_t)(G - 1) * K + c];
 
   // ---- table description -> two-level table (lane 0 of each chunk) ----
   int lg = 0, hsize = -1, x_long = 0;
@@ -574,10 +612,10 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     uint8_t* weights = &S.ring[0][0] + slot * 256;
     if (active && stream == 0) {
       int nsym = 0;
-      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.prim[slot][0]);
+      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tab[slot][0]);
       hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
       if (hsize >= 0) {
-        x_long = fill_lut2(S.prim[slot], S.tail[slot], weights, nsym, lg);
+        x_long = fill_lut2(S.tab[slot], weights, nsym, lg);
         if (x_long < 0) hsize = -1;
       }
       if (hsize < 0) {
@@ -625,101 +663,43 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   if (stream == 3) { s_off += l0 + l1 + l2; s_len = l3; }
   const uint32_t out_off = (uint32_t)stream * seg;
 
-  // ---- the other planes (indexed by group; the slot of the coded group stays unused) ----
-  SidePlane side[G];
+  // ---- the other planes: groups 0 .. G-2 ----
+  constexpr int NS = (G > 1) ? G - 1 : 1;
+  SidePlane side[NS];
   const uint4* hi_block = reinterpret_cast<const uint4*>(((uintptr_t)(cfg.body + cfg.body_len) - 1) & ~(uintptr_t)15);
   if (G > 1) {
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-      if (g != gh) {
-        const uint64_t i = (uint64_t)g * K + c;
-        const ItemDesc t = cfg.items[i];
-        const uint8_t* q;
-        if (t.kind == kRle) {
-          q = cfg.fill + i * kFillBytes;
-          side[g].step = 0;
-        } else {
-          q = cfg.body + t.src_off + out_off;
-          side[g].step = 1;
-        }
-        side[g].shift = (uint32_t)((uintptr_t)q & 15);
-        side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
-        side[g].a = ldg128(side[g].blk);
-        const uint4* nb = side[g].blk + side[g].step;
-        side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+    for (int g = 0; g < G - 1; g++) {
+      const uint64_t i = (uint64_t)g * K + c;
+      const ItemDesc t = cfg.items[i];
+      const uint8_t* q;
+      if (t.kind == kRle) {
+        q = cfg.fill + i * kFillBytes;
+        side[g].step = 0;
+      } else {
+        q = cfg.body + t.src_off + out_off;
+        side[g].step = 1;
       }
+      side[g].shift = (uint32_t)((uintptr_t)q & 15);
+      side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
+      side[g].a = ldg128(side[g].blk);
+      const uint4* nb = side[g].blk + side[g].step;
+      side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
     }
   }
 
   uint8_t* out_c = out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G;
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  const LutTwo lut{S.prim[slot], S.tail[slot], (uint32_t)x_long};
+  const LutTwo lut{S.tab[slot], (uint32_t)x_long};
 
   BitWindow b;
   ok = window_init(b, p + s_off, s_len, cfg.body, S.ring[lane]);
   if (ok) {
     const uint32_t n16 = seg >> 4;
-    for (uint32_t it = 0; it < n16; it++) {
-      // prefetch block k+2 of every side plane (used next iteration)
-      if (G > 1) {
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          if (g != gh) {
-            const uint4* nb = side[g].blk + 2 * side[g].step;
-            side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
-          }
-        }
-      }
-      uint32_t dsym[4];
-      decode16(b, lut, dsym);
-      if (G == 1) {
-        *reinterpret_cast<uint4*>(out_c + 16 * it) = make_uint4(dsym[0], dsym[1], dsym[2], dsym[3]);
-      } else {
-        uint32_t pl[G][4];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          if (g == gh) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) pl[g][q] = dsym[q];
-          } else {
-            take16(side[g].a, side[g].b, side[g].shift, pl[g]);
-          }
-        }
-        if (rot) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) unrotate_planes(pl[G - 2][q], pl[G - 1][q]);
-        }
-        uint32_t w[4 * G];
-        if (G == 2) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            w[2 * q] = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140);
-            w[2 * q + 1] = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const uint32_t t0 = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140), t1 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x5140);
-            const uint32_t t2 = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362), t3 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x7362);
-            w[4 * q] = __byte_perm(t0, t1, 0x5410);
-            w[4 * q + 1] = __byte_perm(t0, t1, 0x7632);
-            w[4 * q + 2] = __byte_perm(t2, t3, 0x5410);
-            w[4 * q + 3] = __byte_perm(t2, t3, 0x7632);
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(out_c + (uint64_t)16 * G * it);
-#pragma unroll
-        for (int q = 0; q < G; q++) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          if (g != gh) {
-            side[g].a = side[g].b;
-            side[g].b = side[g].c;
-            side[g].blk += side[g].step;
-          }
-        }
-      }
-    }
+    const uint32_t n_main = n16 > 2 ? n16 - 2 : 0;  // look-ahead never leaves the plane here
+    uint32_t it = 0;
+    for (; it < n_main; it++) fused_iteration<G, false>(b, lut, side, hi_block, rot, out_c + (uint64_t)16 * G * it);
+    for (; it < n16; it++) fused_iteration<G, true>(b, lut, side, hi_block, rot, out_c + (uint64_t)16 * G * it);
     ok = window_exact(b);
   }
   if (!ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
