@@ -302,3 +302,22 @@ def test_large_round_trip_properties():
     want = O.zipnn_compress(plan["header"], np.frombuffer(raw_bytes(part), dtype=np.uint8), 2, 1, 10, 262144, 0.95, threads=3)
     wcum = want[len(plan["header"]) + 6: len(plan["header"]) + 6 + 48].view(np.uint64).reshape(2, 3)
     assert int(wcum[1, -1]) == int(cum[1, c0 + 2] - cum[1, c0 - 1])
+
+
+def test_pipelined_host_decompress(monkeypatch):
+    """Host streams above a size threshold are decoded slab by slab on two CUDA streams."""
+    import zipnn_b200.zipnn as zz
+    monkeypatch.setattr(zz, "PIPELINE_MIN_BYTES", 1 << 20)
+    monkeypatch.setattr(zz, "PIPELINE_SLAB_BYTES", 3 * 262144)
+    g = torch.Generator().manual_seed(5)
+    for dt, n in ((torch.bfloat16, 5 * 131072 * 2 + 12345), (torch.float32, 11 * 65536 + 7), (torch.float8_e4m3fn, 9 * 131072 + 1)):
+        t = (torch.randn(n, generator=g) * 0.02).to(dt)
+        t[1000:200000] = 0  # RLE planes in some chunks
+        s = ZipNN(input_format="torch").compress(t)
+        back = ZipNN(input_format="torch").decompress(bytes(s))
+        assert back.dtype == dt and raw_bytes(back) == raw_bytes(t)
+        bad = bytearray(bytes(s))
+        bad[-5] = 0 if bad[-5] else 1
+        bad[-1] = 0
+        with pytest.raises(RuntimeError, match="corrupt"):
+            ZipNN(input_format="torch").decompress(bytes(bad))

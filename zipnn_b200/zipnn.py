@@ -480,11 +480,22 @@ def _compress_host(flat_u8, header: bytes, num_buf: int, bits_mode: int, bytes_m
     return memoryview(host.numpy())
 
 
+# Host streams at least this large are decoded slab by slab on two CUDA streams, so the H2D
+# copy of one slab overlaps the decode of the previous one and the D2H copy of the one before
+# (PCIe is full duplex; a 16 GiB bf16 round trip is ~97% copy time).  Tests lower both knobs.
+PIPELINE_MIN_BYTES = 64 << 20
+PIPELINE_SLAB_BYTES = 256 << 20
+
+
 def _decompress_host(body: np.ndarray, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int, orig: int, out=None) -> torch.Tensor:
     _native.require_cuda()
     host = _host_out(orig, out)
     if orig == 0:
         return host
+    if orig >= PIPELINE_MIN_BYTES and orig > PIPELINE_SLAB_BYTES:
+        done = _decompress_host_pipelined(body, num_buf, bits_mode, bytes_mode, chunk, orig, host)
+        if done:
+            return host
     src = _host_tensor(np.ascontiguousarray(body))
     # 64 leading bytes keep the word-granular stream readers inside the allocation
     dev = torch.empty(src.numel() + 64 + 16, dtype=torch.uint8, device="cuda")
@@ -494,3 +505,84 @@ def _decompress_host(body: np.ndarray, num_buf: int, bits_mode: int, bytes_mode:
     host.copy_(dec, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return host
+
+
+def _decompress_host_pipelined(body: np.ndarray, G: int, bits_mode: int, bytes_mode: int, chunk: int, orig: int,
+                               host: torch.Tensor) -> bool:
+    """Chunks are independent, so any chunk range [c0, c1) is a stream of its own once its rows of
+    the type/size tables are rebased (the same construction zipnn_b200.sharded uses across GPUs).
+    Returns False if the stream turns out to need the general-path workspace (caller falls back)."""
+    L = _native.lib()
+    K = (orig + chunk - 1) // chunk
+    body = np.ascontiguousarray(body)
+    if body.size < 9 * G * K:
+        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
+    types = body[: G * K].reshape(G, K)
+    cum = np.frombuffer(body[G * K: 9 * G * K].tobytes(), dtype="<u8").reshape(G, K).astype(np.int64)
+    payload0 = 9 * G * K
+    group_tot = cum[:, -1]
+    if np.any(np.diff(cum, axis=1) < 0) or np.any(cum[:, 0] < 0) or payload0 + int(group_tot.sum()) > body.size:
+        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
+    base = np.concatenate([[0], np.cumsum(group_tot)[:-1]]).astype(np.int64) + payload0
+    per = max(1, PIPELINE_SLAB_BYTES // chunk)
+    slabs = [(c0, min(K, c0 + per)) for c0 in range(0, K, per)]
+    src_t = _host_tensor(body)
+    nst = 2
+    streams = [torch.cuda.Stream() for _ in range(nst)]
+    cur = torch.cuda.current_stream()
+    slab_bytes_max = per * chunk
+    # per-stream device buffers: [64 pad | local body], decoded slab, workspace
+    lbuf = [torch.empty(64 + 9 * G * per + slab_bytes_max + 9 * G * per + 64, dtype=torch.uint8, device="cuda") for _ in range(nst)]
+    obuf = [torch.empty(slab_bytes_max, dtype=torch.uint8, device="cuda") for _ in range(nst)]
+    wsz = _native.decompress_workspace_size(slab_bytes_max, G, chunk)
+    wbuf = [torch.empty(wsz, dtype=torch.uint8, device="cuda") for _ in range(nst)]
+    stage = [torch.empty(9 * G * per + 64, dtype=torch.uint8, pin_memory=True) for _ in range(nst)]
+    staged_evt = [None] * nst
+    errs = torch.zeros(len(slabs), dtype=torch.int32, device="cuda")
+    rc_bad = 0
+    for i, (c0, c1) in enumerate(slabs):
+        k = i % nst
+        st = streams[k]
+        Ks = c1 - c0
+        b0, b1 = c0 * chunk, min(orig, c1 * chunk)
+        lo = cum[:, c0 - 1] if c0 else np.zeros(G, dtype=np.int64)
+        sizes = cum[:, c1 - 1] - lo
+        tables = np.empty(9 * G * Ks, dtype=np.uint8)
+        tables[: G * Ks] = types[:, c0:c1].reshape(-1)
+        tables[G * Ks:] = (cum[:, c0:c1] - lo.reshape(G, 1)).astype("<u8").reshape(-1).view(np.uint8)
+        if staged_evt[k] is not None:
+            staged_evt[k].synchronize()          # the previous H2D out of this staging buffer is done
+        stage[k][: tables.size].copy_(torch.from_numpy(tables))
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            dbody = lbuf[k][64:]
+            dbody[: tables.size].copy_(stage[k][: tables.size], non_blocking=True)
+            staged_evt[k] = torch.cuda.Event()
+            staged_evt[k].record(st)
+            at = tables.size
+            for g in range(G):
+                ln = int(sizes[g])
+                if ln:
+                    s0 = int(base[g] + lo[g])
+                    dbody[at: at + ln].copy_(src_t[s0: s0 + ln], non_blocking=True)
+                    at += ln
+            rc = L.zipnn_b200_decompress(dbody.data_ptr(), at, G, bits_mode, bytes_mode, chunk, b1 - b0,
+                                         obuf[k].data_ptr(), wbuf[k].data_ptr(), wbuf[k].numel(), st.cuda_stream, 0)
+            if rc:
+                rc_bad = rc
+                break
+            errs[i: i + 1].copy_(wbuf[k][:4].view(torch.int32), non_blocking=True)
+            host[b0:b1].copy_(obuf[k][: b1 - b0], non_blocking=True)
+    for st in streams:
+        cur.wait_stream(st)
+    cur.synchronize()
+    if rc_bad:
+        _native.check(rc_bad)
+    flags = int(np.bitwise_or.reduce(errs.cpu().numpy())) if len(slabs) else 0
+    if flags & 1:
+        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
+    if flags & 2:
+        _native.check(_native.E_UNSUPPORTED)
+    if flags & 4:
+        return False  # many multi-group chunks: let the one-shot path size the full workspace
+    return True
