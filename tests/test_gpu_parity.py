@@ -317,7 +317,7 @@ def test_pipelined_host_decompress(monkeypatch):
         back = ZipNN(input_format="torch").decompress(bytes(s))
         assert back.dtype == dt and raw_bytes(back) == raw_bytes(t)
         bad = bytearray(bytes(s))
-        bad[-5] = 0 if bad[-5] else 1
-        bad[-1] = 0
+        hdr_len = 32 + 1 + 1 + 4   # header + 1-D shape with a 4-byte dimension
+        bad[hdr_len + 1] = 9        # a type byte out of range is always detectable
         with pytest.raises(RuntimeError, match="corrupt"):
             ZipNN(input_format="torch").decompress(bytes(bad))

@@ -117,12 +117,12 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
       cfg.items[i] = d;
     }
     // The fused kernel wants the one coded plane to be the top byte plane (the exponent side: what
-    // float tensors produce), and whole, equally long planes whose quarter streams start on
-    // 16-element boundaries: chunk_len a multiple of 64*G.  Anything else goes the general way.
+    // float tensors produce), and whole, equally long planes whose quarter streams are a whole
+    // number of 128-byte output rows: chunk_len a multiple of 512.  Anything else goes the general way.
     uint32_t m = kModePlain;
     if (bad_chunk) {
       m = kModeSkip;  // rejected: nothing may be read through its (untrusted) offsets
-    } else if (nhuf == 1 && last_huf == G - 1 && (chunk_len % (64u * (uint32_t)G)) == 0) {
+    } else if (nhuf == 1 && last_huf == G - 1 && (chunk_len % 512u) == 0) {
       m = kModeFused;
     } else if (nhuf >= 1) {
       m = kModeGeneral;
@@ -498,6 +498,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 struct FusedSmem {
   uint16_t tab[kDecItemsPerWarp][512];             // primary + tail; also scratch for the table parse
   __align__(16) uint8_t ring[32][kRingBytes];      // weights[8][256] alias it during the parse
+  __align__(16) uint8_t stage[32][128];            // one 128-byte output row per lane, 16-byte units XOR-swizzled
 };
 static_assert(sizeof(FseDecSmall) <= 1024, "small tANS scratch must fit in one table slot");
 
@@ -538,9 +539,22 @@ __device__ __forceinline__ void unrotate_planes(uint32_t& lo, uint32_t& hi) {
 // One iteration: 16 symbols of the coded (top) plane + the matching bytes of the G-1 other
 // planes -> 16*G bytes of elements.  kGuard = clamp the look-ahead block loads to the end of
 // the stream buffer (only the last iterations of a stream can reach past it).
+// Output rows.  A lane produces 16*G bytes per iteration, 64 KiB away from its neighbours'
+// data, so direct stores cost one LSU wavefront per lane.  Instead each lane fills a 128-byte
+// row in shared memory (16-byte units XOR-swizzled by the lane so that the 128-bit stores of 8
+// lanes cover 32 banks), and every 8/G iterations the warp writes the 32 rows out with 8 stores
+// that each cover four whole 128-byte lines.
+__device__ __forceinline__ uint4* stage_unit(uint8_t (*stage)[128], int row, int unit) {
+  return reinterpret_cast<uint4*>(&stage[row][((unit ^ row) & 7) * 16]);
+}
+
+// One iteration: 16 symbols of the coded (top) plane + the matching bytes of the G-1 other
+// planes -> 16*G bytes of elements into units [unit0, unit0+G) of the lane's stage row.
+// kGuard = clamp the look-ahead block loads to the end of the stream buffer (only the last
+// iterations of a stream can reach past it).
 template <int G, bool kGuard>
 __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
-                                                const uint4* hi_block, bool rot, uint8_t* dst_bytes) {
+                                                const uint4* hi_block, bool rot, uint8_t (*stage)[128], int lane, int unit0) {
   if (G > 1) {
 #pragma unroll
     for (int g = 0; g < G - 1; g++) {  // block k+2 of every side plane, used next iteration
@@ -552,7 +566,7 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut,
   uint32_t pl[G][4];
   decode16(b, lut, pl[G - 1]);
   if (G == 1) {
-    *reinterpret_cast<uint4*>(dst_bytes) = make_uint4(pl[0][0], pl[0][1], pl[0][2], pl[0][3]);
+    *stage_unit(stage, lane, unit0) = make_uint4(pl[0][0], pl[0][1], pl[0][2], pl[0][3]);
     return;
   }
 #pragma unroll
@@ -579,9 +593,8 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut,
       w[4 * q + 3] = __byte_perm(t2, t3, 0x7632);
     }
   }
-  uint4* dst = reinterpret_cast<uint4*>(dst_bytes);
 #pragma unroll
-  for (int q = 0; q < G; q++) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  for (int q = 0; q < G; q++) *stage_unit(stage, lane, unit0 + q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 #pragma unroll
   for (int g = 0; g < G - 1; g++) {
     side[g].a = side[g].b;
@@ -637,26 +650,29 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     x_long = __shfl_sync(0xffffffffu, x_long, lane & ~3);
     __syncwarp();  // the ring (aliased by weights) is free from here on
   }
-  if (!active || hsize < 0) return;
+  // From here on no lane leaves early: the output flush is a warp-wide exchange.
+  bool live = active && hsize >= 0;
 
   // ---- jump table (huf_decompress.c:283-290) ----
-  const uint8_t* p = cfg.body + d.src_off + hsize;
-  const uint32_t rest = d.src_len - (uint32_t)hsize;
-  bool ok = rest >= 10;
+  const uint8_t* p = cfg.body + d.src_off + (live ? hsize : 0);
+  const uint32_t rest = live ? d.src_len - (uint32_t)hsize : 0;
   uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-  if (ok) {
-    l0 = p[0] | (p[1] << 8);
-    l1 = p[2] | (p[3] << 8);
-    l2 = p[4] | (p[5] << 8);
-    ok = l0 + l1 + l2 + 6 <= rest;
-    l3 = rest - (l0 + l1 + l2 + 6);
-    ok = ok && l0 && l1 && l2 && l3;
+  if (live) {
+    bool ok = rest >= 10;
+    if (ok) {
+      l0 = p[0] | (p[1] << 8);
+      l1 = p[2] | (p[3] << 8);
+      l2 = p[4] | (p[5] << 8);
+      ok = l0 + l1 + l2 + 6 <= rest;
+      l3 = rest - (l0 + l1 + l2 + 6);
+      ok = ok && l0 && l1 && l2 && l3;
+    }
+    if (!ok) {
+      atomicOr(&cfg.ctrl->error, kErrCorrupt);
+      live = false;
+    }
   }
-  if (!ok) {
-    atomicOr(&cfg.ctrl->error, kErrCorrupt);
-    return;
-  }
-  const uint32_t seg = d.dec_len >> 2;  // fused chunks: dec_len % 64 == 0
+  const uint32_t seg = d.dec_len >> 2;  // fused chunks: dec_len % 128 == 0
   uint32_t s_off = 6, s_len = l0;
   if (stream == 1) { s_off += l0; s_len = l1; }
   if (stream == 2) { s_off += l0 + l1; s_len = l2; }
@@ -667,7 +683,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   constexpr int NS = (G > 1) ? G - 1 : 1;
   SidePlane side[NS];
   const uint4* hi_block = reinterpret_cast<const uint4*>(((uintptr_t)(cfg.body + cfg.body_len) - 1) & ~(uintptr_t)15);
-  if (G > 1) {
+  if (G > 1 && live) {
 #pragma unroll
     for (int g = 0; g < G - 1; g++) {
       const uint64_t i = (uint64_t)g * K + c;
@@ -688,21 +704,53 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     }
   }
 
-  uint8_t* out_c = out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G;
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
   const LutTwo lut{S.tab[slot], (uint32_t)x_long};
-
   BitWindow b;
-  ok = window_init(b, p + s_off, s_len, cfg.body, S.ring[lane]);
-  if (ok) {
-    const uint32_t n16 = seg >> 4;
-    const uint32_t n_main = n16 > 2 ? n16 - 2 : 0;  // look-ahead never leaves the plane here
-    uint32_t it = 0;
-    for (; it < n_main; it++) fused_iteration<G, false>(b, lut, side, hi_block, rot, out_c + (uint64_t)16 * G * it);
-    for (; it < n16; it++) fused_iteration<G, true>(b, lut, side, hi_block, rot, out_c + (uint64_t)16 * G * it);
-    ok = window_exact(b);
+  if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
+    atomicOr(&cfg.ctrl->error, kErrCorrupt);
+    live = false;
   }
-  if (!ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+
+  // ---- rows: 128 bytes of output = 128/G elements = kIters iterations of 16 symbols ----
+  constexpr int kIters = 8 / G;
+  const uint32_t my_rows = live ? (seg >> 4) / kIters : 0;
+  uint32_t max_rows = my_rows;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) max_rows = max(max_rows, __shfl_xor_sync(0xffffffffu, max_rows, o));
+  // the 8 stage rows this lane writes out each round: row r*4 + lane/8, 16-byte unit lane%8
+  const uint64_t my_out = (uint64_t)(uintptr_t)(out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G);
+  uint64_t row_out[8];
+  uint32_t row_cnt[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int src = r * 4 + (lane >> 3);
+    row_out[r] = __shfl_sync(0xffffffffu, my_out, src) + (uint64_t)(lane & 7) * 16;
+    row_cnt[r] = __shfl_sync(0xffffffffu, my_rows, src);
+  }
+
+  for (uint32_t row = 0; row < max_rows; row++) {
+    if (row < my_rows) {
+      if (row + 1 < my_rows) {
+#pragma unroll
+        for (int k = 0; k < kIters; k++) fused_iteration<G, false>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
+      } else {  // the look-ahead loads of the last row may reach past the plane
+#pragma unroll
+        for (int k = 0; k < kIters; k++) fused_iteration<G, true>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int src = r * 4 + (lane >> 3);
+      if (row < row_cnt[r]) {
+        const uint4 v = *stage_unit(S.stage, src, lane & 7);
+        *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
+      }
+    }
+    __syncwarp();
+  }
+  if (live && !window_exact(b)) atomicOr(&cfg.ctrl->error, kErrCorrupt);
 }
 
 // ====================================================================================
