@@ -157,28 +157,25 @@ constexpr int kDecItemsPerWarp = 8;
 constexpr int kDecLutLog = 11;  // the reference encoder never exceeds 11 (HUF_TABLELOG_DEFAULT)
 constexpr int kDecLutEntries = 1 << kDecLutLog;
 constexpr uint32_t kRingBytes = 128;
+constexpr uint32_t kRingWords = kRingBytes / 4;
 
 struct DecodeSmem {
   uint16_t lut[kDecItemsPerWarp][kDecLutEntries];  // also scratch for the table parse
-  __align__(16) uint8_t ring[32][kRingBytes];      // per lane; weights[8][256] alias it during the parse
+  __align__(16) uint32_t ring[kRingWords][32];     // word-interleaved per lane; weights[8][256] alias it during the parse
 };
 static_assert(sizeof(FseDec) <= sizeof(uint16_t) * kDecLutEntries, "FseDec must fit in one LUT slot");
-static_assert(32 * kRingBytes >= kDecItemsPerWarp * 256, "weights alias the ring");
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
+static_assert(32 * 128 >= kDecItemsPerWarp * 256, "weights alias the ring");
 
 // Bit window, CPU style (bitstream.h:272-443) on top of the ring: a 64-bit container holding
 // bytes [p, p+8) of the stream and a count `c` of bits already consumed from its top.  A symbol
-// costs: peek = (container << c) >> 53, consume = c += length.  Every 4 symbols (4 x 11 bits
+// costs: peek = (container << c) >> 32, consume = c += length.  Every 4 symbols (4 x 11 bits
 // + 7 <= 64 - 11) the container is re-read at byte granularity: p -= c >> 3, c &= 7.  No branch.
+//
+// The ring is word-interleaved across the warp: word j of lane l lives at ring[j][l], so any
+// 32-bit ring read of a warp touches 32 different banks whatever the lanes' positions are.
+// It is filled by 128-bit global loads issued one iteration before they are stored (all lanes
+// execute the same predicated load/store sequence at the same program point, so the per-warp
+// scoreboard only ever waits for loads that are a whole iteration old).
 struct BitWindow {
   uint64_t cont;         // bytes [p, p+8) of the stream, little endian
   uint32_t c;            // bits consumed from the top of `cont`
@@ -187,22 +184,36 @@ struct BitWindow {
   uint32_t start_bit;    // bit offset (from gbase) of the first stream bit (exact-consumption check)
   const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
   uint32_t floor_off;    // do not request blocks below this offset (start of the stream buffer)
-  const uint8_t* ring;
+  uint32_t* ring;        // &ring[0][lane]; word j at ring[j * 32]
+  uint4 pend[2];         // blocks loaded during the previous iteration, not yet in the ring
+  uint32_t pend_off[2];  // their offsets; 0xFFFFFFFF = none
 };
 
-__device__ __forceinline__ uint32_t ring_word(const uint8_t* ring, uint32_t off) {
-  return *reinterpret_cast<const uint32_t*>(ring + (off & (kRingBytes - 4)));
+__device__ __forceinline__ uint32_t ring_word(const uint32_t* ring, uint32_t off) {
+  return ring[((off >> 2) & (kRingWords - 1)) * 32];
+}
+__device__ __forceinline__ void ring_store(uint32_t* ring, uint32_t off, const uint4& v) {
+  const uint32_t j = (off >> 2) & (kRingWords - 1);  // off % 16 == 0: four consecutive word slots
+  ring[(j + 0) * 32] = v.x;
+  ring[(j + 1) * 32] = v.y;
+  ring[(j + 2) * 32] = v.z;
+  ring[(j + 3) * 32] = v.w;
 }
 
-// Request every 16-byte block that fits in the ring below what is still needed (<= `maxn`).
-__device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
-#pragma unroll 2
-  for (int i = 0; i < maxn; i++) {
+// Put the blocks loaded one iteration ago into the ring, then request up to two more.
+// Block [f, f+16) replaces ring bytes [f+128, f+144): allowed once they lie above the aligned
+// words a reload of the container can still touch, (p & ~3) + 12.
+__device__ __forceinline__ void ring_cycle(BitWindow& b) {
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+    if (b.pend_off[i] != 0xFFFFFFFFu) ring_store(b.ring, b.pend_off[i], b.pend[i]);
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
     const uint32_t f = b.fetch - 16;
-    // block [f, f+16) replaces ring bytes [f+128, f+144): allowed once they lie above the
-    // aligned words a reload of the container can still touch, (p & ~3) + 12
-    if (b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.p + 12) {
-      cp_async16(const_cast<uint8_t*>(b.ring) + (f & (kRingBytes - 1)), b.gbase + f);
+    const bool ok = b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.p + 12;
+    b.pend_off[i] = ok ? f : 0xFFFFFFFFu;
+    if (ok) {
+      b.pend[i] = __ldg(reinterpret_cast<const uint4*>(b.gbase + f));
       b.fetch = f;
     }
   }
@@ -224,10 +235,11 @@ __device__ __forceinline__ void window_reload(BitWindow& b) {
 }
 
 // s points at the stream (len bytes); `lo` is the first readable byte of the buffer.
-__device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo, uint8_t* ring) {
+// ring_lane = &ring[0][lane].
+__device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo, uint32_t* ring_lane) {
   const uint8_t lastb = s[len - 1];
   if (lastb == 0) return false;
-  b.ring = ring;
+  b.ring = ring_lane;
   b.gbase = reinterpret_cast<const uint8_t*>(((uintptr_t)s & ~(uintptr_t)(kRingBytes - 1)) - kRingBytes);
   // (one ring below the stream start keeps every offset the decoder forms non-negative)
   b.floor_off = (b.gbase < lo) ? (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15) : 0u;
@@ -239,9 +251,8 @@ __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint
   b.p = top_byte - 7;
   b.c = 8u * (top_byte + 1) - mark;  // 0..7 bits above the first unread bit
   b.fetch = (top_byte & ~15u) + 16;
-  ring_top_up(b, (int)(kRingBytes / 16));
-  cp_async_commit();
-  cp_async_wait<0>();
+  b.pend_off[0] = b.pend_off[1] = 0xFFFFFFFFu;
+  for (int i = 0; i < (int)(kRingBytes / 32) + 1; i++) ring_cycle(b);  // fill: 2 blocks per cycle, +1 to flush
   window_load(b);
   return true;
 }
@@ -263,13 +274,18 @@ struct LutFull {
 // indexed by all 11 bits (read only by the lanes that need it).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
 constexpr int kTailEntries = 256;
+// The 8 primary tables of a warp are interleaved entry by entry (entry k of chunk i at
+// prim[k][i], 4 bytes each): the lookups of chunk i only ever touch banks {i, i+8, i+16, i+24},
+// and its 4 lanes mostly hit the same few hot entries, so a warp's lookup is ~1.5 wavefronts
+// instead of ~3 for 8 separately laid out tables.
 struct LutTwo {
-  const uint16_t* tab;   // [0,256): primary, [256, 512): tail
+  const uint32_t* prim;  // &prim[0][item]; entry k at prim[k * 8]
+  const uint16_t* tail;  // this chunk's tail table
   uint32_t x_long;
   __device__ __forceinline__ uint32_t get(uint32_t top32) const {
     const uint32_t idx = top32 >> 21;
-    uint32_t e = tab[top32 >> 24];
-    if (idx < x_long) e = tab[256 + idx];
+    uint32_t e = prim[(top32 >> 24) * 8];
+    if (idx < x_long) e = tail[idx];
     return e;
   }
 };
@@ -286,8 +302,7 @@ __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) 
 // issued first so the copies overlap the decode.
 template <class LUT>
 __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t (&o)[4]) {
-  ring_top_up(b, 2);
-  cp_async_commit();
+  ring_cycle(b);
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     window_reload(b);
@@ -295,17 +310,13 @@ __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t 
     const uint32_t e2 = window_decode(b, lut), e3 = window_decode(b, lut);
     o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
   }
-  cp_async_wait<1>();  // everything but the group just committed has landed
 }
 
 template <class LUT>
 __device__ __forceinline__ uint32_t decode1(BitWindow& b, const LUT& lut) {
-  ring_top_up(b, 1);
-  cp_async_commit();
+  ring_cycle(b);
   window_reload(b);
-  const uint32_t s = window_decode(b, lut) & 0xFFu;
-  cp_async_wait<0>();
-  return s;
+  return window_decode(b, lut) & 0xFFu;
 }
 
 // Serial single-symbol table fill, one lane per item (huf_decompress.c:151-183): weights
@@ -341,9 +352,8 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
 
 // Two-level fill.  Returns the tail size (index bound of the long codes), or -1 when the
 // tail does not fit kTailEntries / the table log exceeds 11 (the caller demotes the chunk).
-__device__ __forceinline__ int fill_lut2(uint16_t* tab, const uint8_t* weights, int nsym, int lg) {
-  uint16_t* prim = tab;
-  uint16_t* tail = tab + 256;
+__device__ __forceinline__ int fill_lut2(uint32_t* prim /* &prim[0][item], stride 8 */, uint16_t* tail,
+                                         const uint8_t* weights, int nsym, int lg) {
   if (lg > kDecLutLog) return -1;
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
@@ -372,7 +382,7 @@ __device__ __forceinline__ int fill_lut2(uint16_t* tab, const uint8_t* weights, 
       for (uint32_t q = 0; q < span; q++) tail[u + q] = e;
     } else {
       const uint32_t p0 = u >> 3, pn = span >> 3;
-      for (uint32_t q = 0; q < pn; q++) prim[p0 + q] = e;
+      for (uint32_t q = 0; q < pn; q++) prim[(p0 + q) * 8] = e;
     }
   }
   return (int)x_long;
@@ -391,7 +401,7 @@ __device__ __forceinline__ bool setup_item(DecodeSmem& S, const uint8_t* body, c
                                            int stream, Ctrl* ctrl, StreamSetup& st) {
   const int lane = threadIdx.x;
   int lg = 0, hsize = -1;
-  uint8_t* weights = &S.ring[0][0] + slot * 256;
+  uint8_t* weights = reinterpret_cast<uint8_t*>(&S.ring[0][0]) + slot * 256;
   if (active && stream == 0) {
     int nsym = 0;
     FseDec& D = *reinterpret_cast<FseDec*>(&S.lut[slot][0]);
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
   uint8_t* dst = cfg.planes + ((uint64_t)cfg.slot[c] * cfg.G + g) * cfg.pstride + st.out_off;
   BitWindow b;
   const LutFull lut{S.lut[slot], st.lg};
-  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
+  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, &S.ring[0][lane]);
   if (ok) {
     uint32_t done = 0;
     if ((((uintptr_t)dst) & 15) == 0) {
@@ -496,11 +506,12 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 // Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
 // ====================================================================================
 struct FusedSmem {
-  uint16_t tab[kDecItemsPerWarp][512];             // primary + tail; also scratch for the table parse
-  __align__(16) uint8_t ring[32][kRingBytes];      // weights[8][256] alias it during the parse
+  uint32_t prim[256][kDecItemsPerWarp];            // interleaved primary tables
+  uint16_t tail[kDecItemsPerWarp][kTailEntries];   // also scratch for the table parse
+  __align__(16) uint32_t ring[kRingWords][32];     // weights[8][256] alias it during the parse
   __align__(16) uint8_t stage[32][128];            // one 128-byte output row per lane, 16-byte units XOR-swizzled
 };
-static_assert(sizeof(FseDecSmall) <= 1024, "small tANS scratch must fit in one table slot");
+static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in one tail table");
 
 struct SidePlane {
   const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
@@ -622,13 +633,13 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   // ---- table description -> two-level table (lane 0 of each chunk) ----
   int lg = 0, hsize = -1, x_long = 0;
   {
-    uint8_t* weights = &S.ring[0][0] + slot * 256;
+    uint8_t* weights = reinterpret_cast<uint8_t*>(&S.ring[0][0]) + slot * 256;
     if (active && stream == 0) {
       int nsym = 0;
-      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tab[slot][0]);
+      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tail[slot][0]);
       hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
       if (hsize >= 0) {
-        x_long = fill_lut2(S.tab[slot], weights, nsym, lg);
+        x_long = fill_lut2(&S.prim[0][slot], S.tail[slot], weights, nsym, lg);
         if (x_long < 0) hsize = -1;
       }
       if (hsize < 0) {
@@ -705,9 +716,9 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   }
 
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  const LutTwo lut{S.tab[slot], (uint32_t)x_long};
+  const LutTwo lut{&S.prim[0][slot], S.tail[slot], (uint32_t)x_long};
   BitWindow b;
-  if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
+  if (live && !window_init(b, p + s_off, s_len, cfg.body, &S.ring[0][lane])) {
     atomicOr(&cfg.ctrl->error, kErrCorrupt);
     live = false;
   }
