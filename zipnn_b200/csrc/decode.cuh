@@ -185,8 +185,8 @@ struct BitWindow {
   const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
   uint32_t floor_off;    // do not request blocks below this offset (start of the stream buffer)
   uint32_t* ring;        // &ring[0][lane]; word j at ring[j * 32]
-  uint4 pend[2];         // blocks loaded during the previous iteration, not yet in the ring
-  uint32_t pend_off[2];  // their offsets; 0xFFFFFFFF = none
+  uint4 pend[2][2];         // [parity][k]: blocks loaded two iterations ago, not yet in the ring
+  uint32_t pend_off[2][2];  // their offsets; 0xFFFFFFFF = none
 };
 
 __device__ __forceinline__ uint32_t ring_word(const uint32_t* ring, uint32_t off) {
@@ -200,20 +200,21 @@ __device__ __forceinline__ void ring_store(uint32_t* ring, uint32_t off, const u
   ring[(j + 3) * 32] = v.w;
 }
 
-// Put the blocks loaded one iteration ago into the ring, then request up to two more.
-// Block [f, f+16) replaces ring bytes [f+128, f+144): allowed once they lie above the aligned
-// words a reload of the container can still touch, (p & ~3) + 12.
+// Put the blocks loaded TWO iterations ago (same parity) into the ring, then request up to two
+// more into the same registers.  Block [f, f+16) replaces ring bytes [f+128, f+144): allowed
+// once they lie above the aligned words a reload of the container can still touch, (p & ~3) + 12.
+template <int PAR>
 __device__ __forceinline__ void ring_cycle(BitWindow& b) {
 #pragma unroll
   for (int i = 0; i < 2; i++)
-    if (b.pend_off[i] != 0xFFFFFFFFu) ring_store(b.ring, b.pend_off[i], b.pend[i]);
+    if (b.pend_off[PAR][i] != 0xFFFFFFFFu) ring_store(b.ring, b.pend_off[PAR][i], b.pend[PAR][i]);
 #pragma unroll
   for (int i = 0; i < 2; i++) {
     const uint32_t f = b.fetch - 16;
     const bool ok = b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.p + 12;
-    b.pend_off[i] = ok ? f : 0xFFFFFFFFu;
+    b.pend_off[PAR][i] = ok ? f : 0xFFFFFFFFu;
     if (ok) {
-      b.pend[i] = __ldg(reinterpret_cast<const uint4*>(b.gbase + f));
+      b.pend[PAR][i] = __ldg(reinterpret_cast<const uint4*>(b.gbase + f));
       b.fetch = f;
     }
   }
@@ -251,8 +252,12 @@ __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint
   b.p = top_byte - 7;
   b.c = 8u * (top_byte + 1) - mark;  // 0..7 bits above the first unread bit
   b.fetch = (top_byte & ~15u) + 16;
-  b.pend_off[0] = b.pend_off[1] = 0xFFFFFFFFu;
-  for (int i = 0; i < (int)(kRingBytes / 32) + 1; i++) ring_cycle(b);  // fill: 2 blocks per cycle, +1 to flush
+  b.pend_off[0][0] = b.pend_off[0][1] = b.pend_off[1][0] = b.pend_off[1][1] = 0xFFFFFFFFu;
+#pragma unroll 1
+  for (int i = 0; i < (int)(kRingBytes / 64) + 1; i++) {  // fill: 4 blocks per pair of cycles, +1 pair to flush
+    ring_cycle<0>(b);
+    ring_cycle<1>(b);
+  }
   window_load(b);
   return true;
 }
@@ -274,17 +279,19 @@ struct LutFull {
 // indexed by all 11 bits (read only by the lanes that need it).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
 constexpr int kTailEntries = 256;
-// The 8 primary tables of a warp are interleaved entry by entry (entry k of chunk i at
-// prim[k][i], 4 bytes each): the lookups of chunk i only ever touch banks {i, i+8, i+16, i+24},
-// and its 4 lanes mostly hit the same few hot entries, so a warp's lookup is ~1.5 wavefronts
-// instead of ~3 for 8 separately laid out tables.
+// The 8 primary tables of a warp are interleaved entry by entry, two chunks per 32-bit word:
+// entry k of chunk i is the (i >> 2)-th half of prim[k][i & 3].  The lookups of chunks i and
+// i+4 only ever touch the 8 banks {i&3, (i&3)+4, ...}, and the 4 lanes of a chunk mostly hit
+// the same few hot entries, so a warp's lookup is ~2 wavefronts instead of ~3 for 8 separately
+// laid out tables -- at the same 4 KiB.
 struct LutTwo {
-  const uint32_t* prim;  // &prim[0][item]; entry k at prim[k * 8]
+  const uint32_t* prim;  // &prim[0][item & 3]; entry k in prim[k * 4]
+  uint32_t half_sel;     // PRMT selector extracting this chunk's half, zero-extended
   const uint16_t* tail;  // this chunk's tail table
   uint32_t x_long;
   __device__ __forceinline__ uint32_t get(uint32_t top32) const {
     const uint32_t idx = top32 >> 21;
-    uint32_t e = prim[(top32 >> 24) * 8];
+    uint32_t e = __byte_perm(prim[(top32 >> 24) * 4], 0u, half_sel);
     if (idx < x_long) e = tail[idx];
     return e;
   }
@@ -300,9 +307,9 @@ __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) 
 
 // 16 symbols -> 4 words (symbol j in byte j).  Ring maintenance for the NEXT iterations is
 // issued first so the copies overlap the decode.
-template <class LUT>
+template <int PAR, class LUT>
 __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t (&o)[4]) {
-  ring_cycle(b);
+  ring_cycle<PAR>(b);
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     window_reload(b);
@@ -314,7 +321,8 @@ __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t 
 
 template <class LUT>
 __device__ __forceinline__ uint32_t decode1(BitWindow& b, const LUT& lut) {
-  ring_cycle(b);
+  ring_cycle<0>(b);  // one symbol per call: alternate parities so that stores trail loads by two calls
+  ring_cycle<1>(b);
   window_reload(b);
   return window_decode(b, lut) & 0xFFu;
 }
@@ -352,8 +360,8 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
 
 // Two-level fill.  Returns the tail size (index bound of the long codes), or -1 when the
 // tail does not fit kTailEntries / the table log exceeds 11 (the caller demotes the chunk).
-__device__ __forceinline__ int fill_lut2(uint32_t* prim /* &prim[0][item], stride 8 */, uint16_t* tail,
-                                         const uint8_t* weights, int nsym, int lg) {
+__device__ __forceinline__ int fill_lut2(uint16_t* prim /* this chunk's half of prim[0][item & 3]; entry stride 8 halves */,
+                                         uint16_t* tail, const uint8_t* weights, int nsym, int lg) {
   if (lg > kDecLutLog) return -1;
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
@@ -485,12 +493,15 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
     if ((((uintptr_t)dst) & 15) == 0) {
       const uint32_t n16 = st.count >> 4;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
-      for (uint32_t it = 0; it < n16; it++) {
+      uint32_t it = 0;
+      for (; it + 2 <= n16; it += 2) {
         uint32_t o[4];
-        decode16(b, lut, o);
+        decode16<0>(b, lut, o);
         d4[it] = make_uint4(o[0], o[1], o[2], o[3]);
+        decode16<1>(b, lut, o);
+        d4[it + 1] = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      done = n16 << 4;
+      done = it << 4;
     }
     for (; done < st.count; done++) dst[done] = (uint8_t)decode1(b, lut);
     ok = window_exact(b);
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 // Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
 // ====================================================================================
 struct FusedSmem {
-  uint32_t prim[256][kDecItemsPerWarp];            // interleaved primary tables
+  uint32_t prim[256][4];                           // interleaved primary tables, two chunks per word
   uint16_t tail[kDecItemsPerWarp][kTailEntries];   // also scratch for the table parse
   __align__(16) uint32_t ring[kRingWords][32];     // weights[8][256] alias it during the parse
   __align__(16) uint8_t stage[32][128];            // one 128-byte output row per lane, 16-byte units XOR-swizzled
@@ -517,8 +528,8 @@ struct SidePlane {
   const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
   uint32_t shift;    // byte offset (0..15) of that byte inside the block
   uint32_t step;     // 1 for stream bytes, 0 for an RLE fill block
-  uint4 a, b;        // blocks k, k+1 (k+2 is in flight in `c`)
-  uint4 c;
+  uint4 a, b;        // blocks k, k+1
+  uint4 c, d;        // blocks k+2, k+3 (in flight: each is requested two iterations before use)
 };
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
@@ -563,19 +574,19 @@ __device__ __forceinline__ uint4* stage_unit(uint8_t (*stage)[128], int row, int
 // planes -> 16*G bytes of elements into units [unit0, unit0+G) of the lane's stage row.
 // kGuard = clamp the look-ahead block loads to the end of the stream buffer (only the last
 // iterations of a stream can reach past it).
-template <int G, bool kGuard>
+template <int G, bool kGuard, int PAR>
 __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
                                                 const uint4* hi_block, bool rot, uint8_t (*stage)[128], int lane, int unit0) {
   if (G > 1) {
 #pragma unroll
-    for (int g = 0; g < G - 1; g++) {  // block k+2 of every side plane, used next iteration
-      const uint4* nb = side[g].blk + 2 * side[g].step;
+    for (int g = 0; g < G - 1; g++) {  // block k+3 of every side plane, needed two iterations from now
+      const uint4* nb = side[g].blk + 3 * side[g].step;
       if (kGuard && nb > hi_block) nb = hi_block;
-      side[g].c = ldg128(nb);
+      side[g].d = ldg128(nb);
     }
   }
   uint32_t pl[G][4];
-  decode16(b, lut, pl[G - 1]);
+  decode16<PAR>(b, lut, pl[G - 1]);
   if (G == 1) {
     *stage_unit(stage, lane, unit0) = make_uint4(pl[0][0], pl[0][1], pl[0][2], pl[0][3]);
     return;
@@ -610,6 +621,7 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut,
   for (int g = 0; g < G - 1; g++) {
     side[g].a = side[g].b;
     side[g].b = side[g].c;
+    side[g].c = side[g].d;
     side[g].blk += side[g].step;
   }
 }
@@ -639,7 +651,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tail[slot][0]);
       hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
       if (hsize >= 0) {
-        x_long = fill_lut2(&S.prim[0][slot], S.tail[slot], weights, nsym, lg);
+        x_long = fill_lut2(reinterpret_cast<uint16_t*>(&S.prim[0][slot & 3]) + (slot >> 2), S.tail[slot], weights, nsym, lg);
         if (x_long < 0) hsize = -1;
       }
       if (hsize < 0) {
@@ -712,11 +724,13 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       side[g].a = ldg128(side[g].blk);
       const uint4* nb = side[g].blk + side[g].step;
       side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+      nb = side[g].blk + 2 * side[g].step;
+      side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
     }
   }
 
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  const LutTwo lut{&S.prim[0][slot], S.tail[slot], (uint32_t)x_long};
+  const LutTwo lut{&S.prim[0][slot & 3], (slot >> 2) ? 0x4432u : 0x4410u, S.tail[slot], (uint32_t)x_long};
   BitWindow b;
   if (live && !window_init(b, p + s_off, s_len, cfg.body, &S.ring[0][lane])) {
     atomicOr(&cfg.ctrl->error, kErrCorrupt);
@@ -744,10 +758,16 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     if (row < my_rows) {
       if (row + 1 < my_rows) {
 #pragma unroll
-        for (int k = 0; k < kIters; k++) fused_iteration<G, false>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
+        for (int k = 0; k < kIters; k += 2) {
+          fused_iteration<G, false, 0>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
+          fused_iteration<G, false, 1>(b, lut, side, hi_block, rot, S.stage, lane, (k + 1) * G);
+        }
       } else {  // the look-ahead loads of the last row may reach past the plane
 #pragma unroll
-        for (int k = 0; k < kIters; k++) fused_iteration<G, true>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
+        for (int k = 0; k < kIters; k += 2) {
+          fused_iteration<G, true, 0>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
+          fused_iteration<G, true, 1>(b, lut, side, hi_block, rot, S.stage, lane, (k + 1) * G);
+        }
       }
     }
     __syncwarp();
