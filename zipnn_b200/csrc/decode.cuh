@@ -157,25 +157,28 @@ constexpr int kDecItemsPerWarp = 8;
 constexpr int kDecLutLog = 11;  // the reference encoder never exceeds 11 (HUF_TABLELOG_DEFAULT)
 constexpr int kDecLutEntries = 1 << kDecLutLog;
 constexpr uint32_t kRingBytes = 128;
-constexpr uint32_t kRingWords = kRingBytes / 4;
 
 struct DecodeSmem {
   uint16_t lut[kDecItemsPerWarp][kDecLutEntries];  // also scratch for the table parse
-  __align__(16) uint32_t ring[kRingWords][32];     // word-interleaved per lane; weights[8][256] alias it during the parse
+  __align__(16) uint8_t ring[32][kRingBytes];      // per lane; weights[8][256] alias it during the parse
 };
 static_assert(sizeof(FseDec) <= sizeof(uint16_t) * kDecLutEntries, "FseDec must fit in one LUT slot");
-static_assert(32 * 128 >= kDecItemsPerWarp * 256, "weights alias the ring");
+static_assert(32 * kRingBytes >= kDecItemsPerWarp * 256, "weights alias the ring");
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 // Bit window, CPU style (bitstream.h:272-443) on top of the ring: a 64-bit container holding
 // bytes [p, p+8) of the stream and a count `c` of bits already consumed from its top.  A symbol
-// costs: peek = (container << c) >> 32, consume = c += length.  Every 4 symbols (4 x 11 bits
+// costs: peek = (container << c) >> 53, consume = c += length.  Every 4 symbols (4 x 11 bits
 // + 7 <= 64 - 11) the container is re-read at byte granularity: p -= c >> 3, c &= 7.  No branch.
-//
-// The ring is word-interleaved across the warp: word j of lane l lives at ring[j][l], so any
-// 32-bit ring read of a warp touches 32 different banks whatever the lanes' positions are.
-// It is filled by 128-bit global loads issued one iteration before they are stored (all lanes
-// execute the same predicated load/store sequence at the same program point, so the per-warp
-// scoreboard only ever waits for loads that are a whole iteration old).
 struct BitWindow {
   uint64_t cont;         // bytes [p, p+8) of the stream, little endian
   uint32_t c;            // bits consumed from the top of `cont`
@@ -184,37 +187,22 @@ struct BitWindow {
   uint32_t start_bit;    // bit offset (from gbase) of the first stream bit (exact-consumption check)
   const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
   uint32_t floor_off;    // do not request blocks below this offset (start of the stream buffer)
-  uint32_t* ring;        // &ring[0][lane]; word j at ring[j * 32]
-  uint4 pend[2][2];         // [parity][k]: blocks loaded two iterations ago, not yet in the ring
-  uint32_t pend_off[2][2];  // their offsets; 0xFFFFFFFF = none
+  const uint8_t* ring;
 };
 
-__device__ __forceinline__ uint32_t ring_word(const uint32_t* ring, uint32_t off) {
-  return ring[((off >> 2) & (kRingWords - 1)) * 32];
-}
-__device__ __forceinline__ void ring_store(uint32_t* ring, uint32_t off, const uint4& v) {
-  const uint32_t j = (off >> 2) & (kRingWords - 1);  // off % 16 == 0: four consecutive word slots
-  ring[(j + 0) * 32] = v.x;
-  ring[(j + 1) * 32] = v.y;
-  ring[(j + 2) * 32] = v.z;
-  ring[(j + 3) * 32] = v.w;
+__device__ __forceinline__ uint32_t ring_word(const uint8_t* ring, uint32_t off) {
+  return *reinterpret_cast<const uint32_t*>(ring + (off & (kRingBytes - 4)));
 }
 
-// Put the blocks loaded TWO iterations ago (same parity) into the ring, then request up to two
-// more into the same registers.  Block [f, f+16) replaces ring bytes [f+128, f+144): allowed
-// once they lie above the aligned words a reload of the container can still touch, (p & ~3) + 12.
-template <int PAR>
-__device__ __forceinline__ void ring_cycle(BitWindow& b) {
-#pragma unroll
-  for (int i = 0; i < 2; i++)
-    if (b.pend_off[PAR][i] != 0xFFFFFFFFu) ring_store(b.ring, b.pend_off[PAR][i], b.pend[PAR][i]);
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
+// Request every 16-byte block that fits in the ring below what is still needed (<= `maxn`).
+__device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
+#pragma unroll 2
+  for (int i = 0; i < maxn; i++) {
     const uint32_t f = b.fetch - 16;
-    const bool ok = b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.p + 12;
-    b.pend_off[PAR][i] = ok ? f : 0xFFFFFFFFu;
-    if (ok) {
-      b.pend[PAR][i] = __ldg(reinterpret_cast<const uint4*>(b.gbase + f));
+    // block [f, f+16) replaces ring bytes [f+128, f+144): allowed once they lie above the
+    // aligned words a reload of the container can still touch, (p & ~3) + 12
+    if (b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.p + 12) {
+      cp_async16(const_cast<uint8_t*>(b.ring) + (f & (kRingBytes - 1)), b.gbase + f);
       b.fetch = f;
     }
   }
@@ -236,11 +224,10 @@ __device__ __forceinline__ void window_reload(BitWindow& b) {
 }
 
 // s points at the stream (len bytes); `lo` is the first readable byte of the buffer.
-// ring_lane = &ring[0][lane].
-__device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo, uint32_t* ring_lane) {
+__device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo, uint8_t* ring) {
   const uint8_t lastb = s[len - 1];
   if (lastb == 0) return false;
-  b.ring = ring_lane;
+  b.ring = ring;
   b.gbase = reinterpret_cast<const uint8_t*>(((uintptr_t)s & ~(uintptr_t)(kRingBytes - 1)) - kRingBytes);
   // (one ring below the stream start keeps every offset the decoder forms non-negative)
   b.floor_off = (b.gbase < lo) ? (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15) : 0u;
@@ -252,12 +239,9 @@ __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint
   b.p = top_byte - 7;
   b.c = 8u * (top_byte + 1) - mark;  // 0..7 bits above the first unread bit
   b.fetch = (top_byte & ~15u) + 16;
-  b.pend_off[0][0] = b.pend_off[0][1] = b.pend_off[1][0] = b.pend_off[1][1] = 0xFFFFFFFFu;
-#pragma unroll 1
-  for (int i = 0; i < (int)(kRingBytes / 64) + 1; i++) {  // fill: 4 blocks per pair of cycles, +1 pair to flush
-    ring_cycle<0>(b);
-    ring_cycle<1>(b);
-  }
+  ring_top_up(b, (int)(kRingBytes / 16));
+  cp_async_commit();
+  cp_async_wait<0>();
   window_load(b);
   return true;
 }
@@ -279,20 +263,13 @@ struct LutFull {
 // indexed by all 11 bits (read only by the lanes that need it).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
 constexpr int kTailEntries = 256;
-// The 8 primary tables of a warp are interleaved entry by entry, two chunks per 32-bit word:
-// entry k of chunk i is the (i >> 2)-th half of prim[k][i & 3].  The lookups of chunks i and
-// i+4 only ever touch the 8 banks {i&3, (i&3)+4, ...}, and the 4 lanes of a chunk mostly hit
-// the same few hot entries, so a warp's lookup is ~2 wavefronts instead of ~3 for 8 separately
-// laid out tables -- at the same 4 KiB.
 struct LutTwo {
-  const uint32_t* prim;  // &prim[0][item & 3]; entry k in prim[k * 4]
-  uint32_t half_sel;     // PRMT selector extracting this chunk's half, zero-extended
-  const uint16_t* tail;  // this chunk's tail table
+  const uint16_t* tab;   // [0,256): primary, [256, 512): tail
   uint32_t x_long;
   __device__ __forceinline__ uint32_t get(uint32_t top32) const {
     const uint32_t idx = top32 >> 21;
-    uint32_t e = __byte_perm(prim[(top32 >> 24) * 4], 0u, half_sel);
-    if (idx < x_long) e = tail[idx];
+    uint32_t e = tab[top32 >> 24];
+    if (idx < x_long) e = tab[256 + idx];
     return e;
   }
 };
@@ -307,9 +284,10 @@ __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) 
 
 // 16 symbols -> 4 words (symbol j in byte j).  Ring maintenance for the NEXT iterations is
 // issued first so the copies overlap the decode.
-template <int PAR, class LUT>
+template <class LUT>
 __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t (&o)[4]) {
-  ring_cycle<PAR>(b);
+  ring_top_up(b, 2);
+  cp_async_commit();
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     window_reload(b);
@@ -317,14 +295,17 @@ __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t 
     const uint32_t e2 = window_decode(b, lut), e3 = window_decode(b, lut);
     o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
   }
+  cp_async_wait<1>();  // everything but the group just committed has landed
 }
 
 template <class LUT>
 __device__ __forceinline__ uint32_t decode1(BitWindow& b, const LUT& lut) {
-  ring_cycle<0>(b);  // one symbol per call: alternate parities so that stores trail loads by two calls
-  ring_cycle<1>(b);
+  ring_top_up(b, 1);
+  cp_async_commit();
   window_reload(b);
-  return window_decode(b, lut) & 0xFFu;
+  const uint32_t s = window_decode(b, lut) & 0xFFu;
+  cp_async_wait<0>();
+  return s;
 }
 
 // Serial single-symbol table fill, one lane per item (huf_decompress.c:151-183): weights
@@ -360,8 +341,9 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
 
 // Two-level fill.  Returns the tail size (index bound of the long codes), or -1 when the
 // tail does not fit kTailEntries / the table log exceeds 11 (the caller demotes the chunk).
-__device__ __forceinline__ int fill_lut2(uint16_t* prim /* this chunk's half of prim[0][item & 3]; entry stride 8 halves */,
-                                         uint16_t* tail, const uint8_t* weights, int nsym, int lg) {
+__device__ __forceinline__ int fill_lut2(uint16_t* tab, const uint8_t* weights, int nsym, int lg) {
+  uint16_t* prim = tab;
+  uint16_t* tail = tab + 256;
   if (lg > kDecLutLog) return -1;
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
@@ -390,7 +372,7 @@ __device__ __forceinline__ int fill_lut2(uint16_t* prim /* this chunk's half of 
       for (uint32_t q = 0; q < span; q++) tail[u + q] = e;
     } else {
       const uint32_t p0 = u >> 3, pn = span >> 3;
-      for (uint32_t q = 0; q < pn; q++) prim[(p0 + q) * 8] = e;
+      for (uint32_t q = 0; q < pn; q++) prim[p0 + q] = e;
     }
   }
   return (int)x_long;
@@ -409,7 +391,7 @@ __device__ __forceinline__ bool setup_item(DecodeSmem& S, const uint8_t* body, c
                                            int stream, Ctrl* ctrl, StreamSetup& st) {
   const int lane = threadIdx.x;
   int lg = 0, hsize = -1;
-  uint8_t* weights = reinterpret_cast<uint8_t*>(&S.ring[0][0]) + slot * 256;
+  uint8_t* weights = &S.ring[0][0] + slot * 256;
   if (active && stream == 0) {
     int nsym = 0;
     FseDec& D = *reinterpret_cast<FseDec*>(&S.lut[slot][0]);
@@ -487,21 +469,18 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
   uint8_t* dst = cfg.planes + ((uint64_t)cfg.slot[c] * cfg.G + g) * cfg.pstride + st.out_off;
   BitWindow b;
   const LutFull lut{S.lut[slot], st.lg};
-  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, &S.ring[0][lane]);
+  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
   if (ok) {
     uint32_t done = 0;
     if ((((uintptr_t)dst) & 15) == 0) {
       const uint32_t n16 = st.count >> 4;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
-      uint32_t it = 0;
-      for (; it + 2 <= n16; it += 2) {
+      for (uint32_t it = 0; it < n16; it++) {
         uint32_t o[4];
-        decode16<0>(b, lut, o);
+        decode16(b, lut, o);
         d4[it] = make_uint4(o[0], o[1], o[2], o[3]);
-        decode16<1>(b, lut, o);
-        d4[it + 1] = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      done = it << 4;
+      done = n16 << 4;
     }
     for (; done < st.count; done++) dst[done] = (uint8_t)decode1(b, lut);
     ok = window_exact(b);
@@ -517,19 +496,18 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 // Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
 // ====================================================================================
 struct FusedSmem {
-  uint32_t prim[256][4];                           // interleaved primary tables, two chunks per word
-  uint16_t tail[kDecItemsPerWarp][kTailEntries];   // also scratch for the table parse
-  __align__(16) uint32_t ring[kRingWords][32];     // weights[8][256] alias it during the parse
+  uint16_t tab[kDecItemsPerWarp][512];             // primary + tail; also scratch for the table parse
+  __align__(16) uint8_t ring[32][kRingBytes];      // weights[8][256] alias it during the parse
   __align__(16) uint8_t stage[32][128];            // one 128-byte output row per lane, 16-byte units XOR-swizzled
 };
-static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in one tail table");
+static_assert(sizeof(FseDecSmall) <= 1024, "small tANS scratch must fit in one table slot");
 
 struct SidePlane {
   const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
   uint32_t shift;    // byte offset (0..15) of that byte inside the block
   uint32_t step;     // 1 for stream bytes, 0 for an RLE fill block
-  uint4 a, b;        // blocks k, k+1
-  uint4 c, d;        // blocks k+2, k+3 (in flight: each is requested two iterations before use)
+  uint4 a, b;        // blocks k, k+1 (k+2 is in flight in `c`)
+  uint4 c;
 };
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
@@ -574,19 +552,19 @@ __device__ __forceinline__ uint4* stage_unit(uint8_t (*stage)[128], int row, int
 // planes -> 16*G bytes of elements into units [unit0, unit0+G) of the lane's stage row.
 // kGuard = clamp the look-ahead block loads to the end of the stream buffer (only the last
 // iterations of a stream can reach past it).
-template <int G, bool kGuard, int PAR>
+template <int G, bool kGuard>
 __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
                                                 const uint4* hi_block, bool rot, uint8_t (*stage)[128], int lane, int unit0) {
   if (G > 1) {
 #pragma unroll
-    for (int g = 0; g < G - 1; g++) {  // block k+3 of every side plane, needed two iterations from now
-      const uint4* nb = side[g].blk + 3 * side[g].step;
+    for (int g = 0; g < G - 1; g++) {  // block k+2 of every side plane, used next iteration
+      const uint4* nb = side[g].blk + 2 * side[g].step;
       if (kGuard && nb > hi_block) nb = hi_block;
-      side[g].d = ldg128(nb);
+      side[g].c = ldg128(nb);
     }
   }
   uint32_t pl[G][4];
-  decode16<PAR>(b, lut, pl[G - 1]);
+  decode16(b, lut, pl[G - 1]);
   if (G == 1) {
     *stage_unit(stage, lane, unit0) = make_uint4(pl[0][0], pl[0][1], pl[0][2], pl[0][3]);
     return;
@@ -621,7 +599,6 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut,
   for (int g = 0; g < G - 1; g++) {
     side[g].a = side[g].b;
     side[g].b = side[g].c;
-    side[g].c = side[g].d;
     side[g].blk += side[g].step;
   }
 }
@@ -645,13 +622,13 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   // ---- table description -> two-level table (lane 0 of each chunk) ----
   int lg = 0, hsize = -1, x_long = 0;
   {
-    uint8_t* weights = reinterpret_cast<uint8_t*>(&S.ring[0][0]) + slot * 256;
+    uint8_t* weights = &S.ring[0][0] + slot * 256;
     if (active && stream == 0) {
       int nsym = 0;
-      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tail[slot][0]);
+      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tab[slot][0]);
       hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
       if (hsize >= 0) {
-        x_long = fill_lut2(reinterpret_cast<uint16_t*>(&S.prim[0][slot & 3]) + (slot >> 2), S.tail[slot], weights, nsym, lg);
+        x_long = fill_lut2(S.tab[slot], weights, nsym, lg);
         if (x_long < 0) hsize = -1;
       }
       if (hsize < 0) {
@@ -724,15 +701,13 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       side[g].a = ldg128(side[g].blk);
       const uint4* nb = side[g].blk + side[g].step;
       side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
-      nb = side[g].blk + 2 * side[g].step;
-      side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
     }
   }
 
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  const LutTwo lut{&S.prim[0][slot & 3], (slot >> 2) ? 0x4432u : 0x4410u, S.tail[slot], (uint32_t)x_long};
+  const LutTwo lut{S.tab[slot], (uint32_t)x_long};
   BitWindow b;
-  if (live && !window_init(b, p + s_off, s_len, cfg.body, &S.ring[0][lane])) {
+  if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
     atomicOr(&cfg.ctrl->error, kErrCorrupt);
     live = false;
   }
@@ -758,16 +733,10 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     if (row < my_rows) {
       if (row + 1 < my_rows) {
 #pragma unroll
-        for (int k = 0; k < kIters; k += 2) {
-          fused_iteration<G, false, 0>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
-          fused_iteration<G, false, 1>(b, lut, side, hi_block, rot, S.stage, lane, (k + 1) * G);
-        }
+        for (int k = 0; k < kIters; k++) fused_iteration<G, false>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
       } else {  // the look-ahead loads of the last row may reach past the plane
 #pragma unroll
-        for (int k = 0; k < kIters; k += 2) {
-          fused_iteration<G, true, 0>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
-          fused_iteration<G, true, 1>(b, lut, side, hi_block, rot, S.stage, lane, (k + 1) * G);
-        }
+        for (int k = 0; k < kIters; k++) fused_iteration<G, true>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
       }
     }
     __syncwarp();
