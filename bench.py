@@ -326,7 +326,7 @@ def run_ours(args, rank, local_rank, world):
     G = 1 if t.element_size() == 1 else (2 if t.element_size() == 2 else 4)
     huf_payload = Cb - (N // G) * (G - 1) if G > 1 else Cb  # bytes of the Huffman-coded group(s) (the others are stored raw)
     algo = {  # algorithmic bytes per launch, see DESIGN.md "kernels"
-        "k_encode_stats": N,                    # reads every input byte once
+        "k_encode_hist": N,                     # reads every input byte once
         "k_encode_write": N + Cb,               # reads the input again, writes the stream
         "k_huf_decode_fused": Cb + N,           # reads the whole stream, writes the elements (fused decode + regroup)
     }

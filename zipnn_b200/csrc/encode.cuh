@@ -47,43 +47,122 @@ __device__ __forceinline__ uint32_t rot_byte_at(const uint8_t* __restrict__ in_c
 }
 
 // =====================================================================================
-// pass A
+// pass A1: histograms.  Pure streaming: every input byte is read once (128-bit loads, four in
+// flight per thread), rotated, and counted with one shared-memory atomic.
+//
+// Counter layout rep[g][bin][col], col = lane % R, 32-bit counters: a warp's 32 atomics go to
+// 32 / (32/R) distinct columns, so two lanes can only collide when they hold the same byte
+// value -- and the address is one shift + one LOP3 from the loaded word (3 instructions per
+// byte including the atomic; the first version spent 11).  Per stream quarter the columns are
+// folded into hist[item][stream][256] (u16) in global memory for pass A2.
 // =====================================================================================
-// Histogram replicas: every lane of a warp owns a column, so the 32 shared-memory atomics of
-// one warp instruction always hit 32 different banks (word index = row * R + lane % R, R = 32;
-// for four groups R = 16 to stay inside shared memory, which costs at most a 2-way conflict).
-// Two 16-bit counters share a word: a stream quarter holds at most 32768 symbols.
 template <int G>
-struct StatsCfg {
-  static constexpr int R = (G == 4) ? 16 : 32;
+struct HistCfg {
+  static constexpr int R = (G == 4) ? 8 : 16;          // columns per bin
+  static constexpr int kShift = (G == 4) ? 5 : 6;      // log2(R * 4): byte offset of a bin
 };
 
 template <int G>
-struct StatsSmem {
-  uint32_t rep[G][128][StatsCfg<G>::R];
-  uint16_t hist[G][4][256];  // per stream
-  uint32_t total[G][256];
-  uint8_t nb[G][256];
-  uint8_t nzsym[G][256];
-  TreeScratch tree[G];
+struct HistSmem {
+  uint32_t rep[G][256][HistCfg<G>::R];
 };
 
 template <int G>
-__device__ __forceinline__ void hist_add(StatsSmem<G>& S, int g, int col, uint32_t b) {
-  atomicAdd(&S.rep[g][b >> 1][col], 1u << (16 * (b & 1)));
+__global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk,
+                                                             uint64_t K, int bits_mode, uint16_t* __restrict__ hist) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HistSmem<G>& S = *reinterpret_cast<HistSmem<G>*>(smem_raw);
+  constexpr int R = HistCfg<G>::R;
+  constexpr int kShift = HistCfg<G>::kShift;
+  constexpr uint32_t kBinMask = 0xFFu << kShift;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t col_bytes = (uint32_t)(lane % R) * 4;
+  unsigned char* const rep_base = reinterpret_cast<unsigned char*>(&S.rep[0][0][0]);
+  for (int i = tid; i < G * 256 * R; i += kEncThreads) (&S.rep[0][0][0])[i] = 0;
+  __syncthreads();
+  for (uint64_t c = blockIdx.x; c < K; c += gridDim.x) {
+    const uint8_t* in_c = in + c * (uint64_t)chunk;
+    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
+    const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;
+    const bool fast = (chunk_len % 64u) == 0;
+    for (int q = 0; q < 4; q++) {
+      if (fast) {
+        const uint32_t qbytes = chunk_len >> 2;  // bytes of input per stream quarter
+        const uint4* src = reinterpret_cast<const uint4*>(in_c + (uint64_t)q * qbytes);
+        const uint32_t nvec = qbytes >> 4;
+        for (uint32_t u0 = 0; u0 < nvec; u0 += 4 * kEncThreads) {
+          uint4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t u = u0 + k * kEncThreads + tid;
+            v[k] = (u < nvec) ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (u0 + k * kEncThreads + tid < nvec) {
+              uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                if (rot_words) w[i] = rot_word<G>(w[i]);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                  // byte b of the word -> (bin << kShift) | column, without extracting the byte
+                  const int sh = 8 * b - kShift;
+                  const uint32_t t = sh >= 0 ? (w[i] >> sh) : (w[i] << (-sh));
+                  const uint32_t off = (t & kBinMask) | col_bytes;
+                  atomicAdd(reinterpret_cast<uint32_t*>(rep_base + ((4 * i + b) % G) * (256 * R * 4) + off), 1u);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        for (int g = 0; g < G; g++) {
+          const uint32_t pl = plane_len(chunk_len, G, g);
+          const uint32_t seg = (pl + 3) >> 2;
+          const uint32_t j0 = min(pl, (uint32_t)q * seg), j1 = (q == 3) ? pl : min(pl, j0 + seg);
+          for (uint32_t j = j0 + tid; j < j1; j += kEncThreads)
+            atomicAdd(&S.rep[g][rot_byte_at<G>(in_c, chunk_len, rot_words, j * G + g)][lane % R], 1u);
+        }
+      }
+      __syncthreads();
+      // fold the columns of each bin (and clear them); thread t owns bin t of every group
+      for (int g = 0; g < G; g++) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int rr = (r + tid) % R;
+          sum += S.rep[g][tid][rr];
+          S.rep[g][tid][rr] = 0;
+        }
+        hist[(((uint64_t)g * K + c) * 4 + q) * 256 + tid] = (uint16_t)min(sum, 65535u);
+      }
+      __syncthreads();
+    }
+  }
 }
 
-// One warp: everything the reference does per block after the histogram
-// (huf_compress.c:671-724 + csrc/zipnn_core.c:371-385).
-template <int G>
-__device__ void warp_block_decision(StatsSmem<G>& S, int g, uint32_t plen, uint32_t chunk_cap, double thr,
-                                    uint8_t* type_out, uint32_t* size_out, EncSave* save) {
+// =====================================================================================
+// pass A2: one warp per (group, chunk) item: everything the reference does per block after
+// the histogram (huf_compress.c:671-724 + csrc/zipnn_core.c:371-385).
+// =====================================================================================
+struct TableWarp {
+  uint16_t hist[4][256];
+  uint32_t total[256];
+  uint8_t nb[256];
+  uint8_t nzsym[256];
+  TreeScratch tree;
+};
+constexpr int kTableWarps = 4;
+
+__device__ void warp_block_decision(TableWarp& S, uint32_t plen, double thr, uint8_t* type_out, uint32_t* size_out,
+                                    EncSave* save) {
   const int lane = threadIdx.x & 31;
-  uint32_t* total = S.total[g];
+  uint32_t* total = S.total;
   uint32_t largest = 0;
   int max_sym = -1;
   for (int s = lane; s < 256; s += 32) {
-    const uint32_t t = (uint32_t)S.hist[g][0][s] + S.hist[g][1][s] + S.hist[g][2][s] + S.hist[g][3][s];
+    const uint32_t t = (uint32_t)S.hist[0][s] + S.hist[1][s] + S.hist[2][s] + S.hist[3][s];
     total[s] = t;
     largest = max(largest, t);
     if (t) max_sym = s;
@@ -115,8 +194,8 @@ __device__ void warp_block_decision(StatsSmem<G>& S, int g, uint32_t plen, uint3
   }
   if (huf) {
     // ---- order the present symbols: count descending, symbol ascending ----
-    TreeScratch& T = S.tree[g];
-    uint8_t* nz = S.nzsym[g];
+    TreeScratch& T = S.tree;
+    uint8_t* nz = S.nzsym;
     int k = 0;
     for (int base = 0; base < 256; base += 32) {
       const int s = base + lane;
@@ -140,8 +219,8 @@ __device__ void warp_block_decision(StatsSmem<G>& S, int g, uint32_t plen, uint3
     int lg = 0, hsize = -1;
     if (lane == 0) {
       const int want = fse_pick_log(kHufLogDefault, plen, (uint32_t)max_sym, 1);
-      lg = huf_lengths_from_sorted(T, k - 1, want, S.nb[g]);
-      hsize = huf_write_table(T, S.nb[g], max_sym, lg);
+      lg = huf_lengths_from_sorted(T, k - 1, want, S.nb);
+      hsize = huf_write_table(T, S.nb, max_sym, lg);
     }
     lg = __shfl_sync(0xffffffffu, lg, 0);
     hsize = __shfl_sync(0xffffffffu, hsize, 0);
@@ -149,9 +228,9 @@ __device__ void warp_block_decision(StatsSmem<G>& S, int g, uint32_t plen, uint3
     if (hsize > 0 && (uint32_t)hsize + 12 < plen && plen >= 12) {
       uint32_t bits[4] = {0, 0, 0, 0};
       for (int s = lane; s <= max_sym; s += 32) {
-        const uint32_t l = S.nb[g][s];
+        const uint32_t l = S.nb[s];
 #pragma unroll
-        for (int q = 0; q < 4; q++) bits[q] += (uint32_t)S.hist[g][q][s] * l;
+        for (int q = 0; q < 4; q++) bits[q] += (uint32_t)S.hist[q][s] * l;
       }
 #pragma unroll
       for (int q = 0; q < 4; q++)
@@ -163,11 +242,11 @@ __device__ void warp_block_decision(StatsSmem<G>& S, int g, uint32_t plen, uint3
         sb[q] = (bits[q] >> 3) + 1;  // ceil((bits + end mark) / 8), bitstream.h:254-260
         csize += sb[q];
       }
-      (void)chunk_cap;  // dst capacity (= chunk) can only bind when the block is kept raw anyway
+      // (the reference's dst capacity, = chunk, can only bind when the block is kept raw anyway)
       if (csize < plen - 1 && (double)csize < (double)plen * thr) {  // huf_compress.c:625, zipnn_core.c:371-373
         type = 1;
         size = csize;
-        for (int s = lane; s < 256; s += 32) save->nb[s] = S.nb[g][s];
+        for (int s = lane; s < 256; s += 32) save->nb[s] = S.nb[s];
         for (int i = lane; i < hsize; i += 32) save->hdr[i] = T.hdr[i];
         if (lane == 0) {
           save->hsize = (uint32_t)hsize;
@@ -185,79 +264,25 @@ __device__ void warp_block_decision(StatsSmem<G>& S, int g, uint32_t plen, uint3
 }
 
 template <int G>
-__global__ void __launch_bounds__(kEncThreads) k_encode_stats(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk,
-                                                              uint64_t K, int bits_mode, double thr, uint8_t* types,
-                                                              uint32_t* sizes, EncSave* saves) {
+__global__ void __launch_bounds__(kTableWarps * 32) k_encode_table(const uint16_t* __restrict__ hist, uint64_t n, uint32_t chunk,
+                                                                   uint64_t K, double thr, uint8_t* types, uint32_t* sizes,
+                                                                   EncSave* saves) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  StatsSmem<G>& S = *reinterpret_cast<StatsSmem<G>*>(smem_raw);
-  constexpr int R = StatsCfg<G>::R;
-  const int tid = threadIdx.x, lane = tid & 31, col = lane % R;
-  for (int i = tid; i < G * 128 * R; i += kEncThreads) (&S.rep[0][0][0])[i] = 0;
-  __syncthreads();
-  for (uint64_t c = blockIdx.x; c < K; c += gridDim.x) {
-    const uint8_t* in_c = in + c * (uint64_t)chunk;
+  TableWarp& S = reinterpret_cast<TableWarp*>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const uint64_t nitems = (uint64_t)G * K;
+  for (uint64_t item = (uint64_t)blockIdx.x * kTableWarps + (threadIdx.x >> 5); item < nitems;
+       item += (uint64_t)gridDim.x * kTableWarps) {
+    const int g = (int)(item / K);
+    const uint64_t c = item - (uint64_t)g * K;
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
-    const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;
-    const bool fast = (chunk_len % 64u) == 0;
-    for (int q = 0; q < 4; q++) {
-      if (fast) {
-        const uint32_t qbytes = chunk_len >> 2;  // bytes of input per stream quarter
-        const uint4* src = reinterpret_cast<const uint4*>(in_c + (uint64_t)q * qbytes);
-        const uint32_t nvec = qbytes >> 4;
-        for (uint32_t u0 = 0; u0 < nvec; u0 += 4 * kEncThreads) {
-          uint4 v[4];
+    const uint4* src = reinterpret_cast<const uint4*>(hist + item * 1024);
+    uint4* dst = reinterpret_cast<uint4*>(&S.hist[0][0]);
 #pragma unroll
-          for (int k = 0; k < 4; k++) {  // four loads in flight per thread
-            const uint32_t u = u0 + k * kEncThreads + tid;
-            v[k] = (u < nvec) ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            if (u0 + k * kEncThreads + tid < nvec) {
-              uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                if (rot_words) w[i] = rot_word<G>(w[i]);
-#pragma unroll
-                for (int b = 0; b < 4; b++) hist_add<G>(S, (4 * i + b) % G, col, (w[i] >> (8 * b)) & 0xFFu);
-              }
-            }
-          }
-        }
-      } else {
-        for (int g = 0; g < G; g++) {
-          const uint32_t pl = plane_len(chunk_len, G, g);
-          const uint32_t seg = (pl + 3) >> 2;
-          const uint32_t j0 = min(pl, (uint32_t)q * seg), j1 = (q == 3) ? pl : min(pl, j0 + seg);
-          for (uint32_t j = j0 + tid; j < j1; j += kEncThreads)
-            hist_add<G>(S, g, col, rot_byte_at<G>(in_c, chunk_len, rot_words, j * G + g));
-        }
-      }
-      __syncthreads();
-      // fold the replicas of each bin pair (and clear them for the next quarter); the lane
-      // rotation keeps the 32 reads of a warp on 32 different banks
-      for (int i = tid; i < G * 128; i += kEncThreads) {
-        const int g = i >> 7, row = i & 127;
-        uint32_t lo = 0, hi = 0;
-#pragma unroll 8
-        for (int r = 0; r < R; r++) {
-          const int rr = (r + lane) % R;
-          const uint32_t wv = S.rep[g][row][rr];
-          S.rep[g][row][rr] = 0;
-          lo += wv & 0xFFFFu;
-          hi += wv >> 16;
-        }
-        S.hist[g][q][2 * row] = (uint16_t)lo;
-        S.hist[g][q][2 * row + 1] = (uint16_t)hi;
-      }
-      __syncthreads();
-    }
-    const int warp = tid >> 5;
-    if (warp < G) {
-      const uint64_t item = (uint64_t)warp * K + c;
-      warp_block_decision<G>(S, warp, plane_len(chunk_len, G, warp), chunk, thr, types + item, sizes + item, saves + item);
-    }
-    __syncthreads();
+    for (int i = 0; i < 4; i++) dst[lane + 32 * i] = __ldg(src + lane + 32 * i);
+    __syncwarp();
+    warp_block_decision(S, plane_len(chunk_len, G, g), thr, types + item, sizes + item, saves + item);
+    __syncwarp();
   }
 }
 
