@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
 // pass A2: one warp per (group, chunk) item: everything the reference does per block after
 // the histogram (huf_compress.c:671-724 + csrc/zipnn_core.c:371-385).
 // =====================================================================================
-struct TableWarp {
+struct __align__(16) TableWarp {
   uint16_t hist[4][256];
   uint32_t total[256];
   uint8_t nb[256];
