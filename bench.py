@@ -327,7 +327,7 @@ def run_ours(args, rank, local_rank, world):
     huf_payload = Cb - (N // G) * (G - 1) if G > 1 else Cb  # bytes of the Huffman-coded group(s) (the others are stored raw)
     algo = {  # algorithmic bytes per launch, see DESIGN.md "kernels"
         "k_encode_hist": N,                     # reads every input byte once
-        "k_encode_write": N + Cb,               # reads the input again, writes the stream
+        "k_encode_write_warp": N + Cb,               # reads the input again, writes the stream
         "k_huf_decode_fused": Cb + N,           # reads the whole stream, writes the elements (fused decode + regroup)
     }
     dom_ms = per_launch[dom][0]

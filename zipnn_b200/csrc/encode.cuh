@@ -450,15 +450,20 @@ template <int G>
 __global__ void __launch_bounds__(kEncThreads) k_encode_write(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk, uint64_t K,
                                                               int bits_mode, const uint8_t* __restrict__ types,
                                                               const uint32_t* __restrict__ sizes, const EncSave* __restrict__ saves,
-                                                              const uint64_t* __restrict__ item_off, uint8_t* out) {
+                                                              const uint64_t* __restrict__ item_off, uint8_t* out,
+                                                              int only_ragged) {
   __shared__ WriteSmem S;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t nitems = (uint64_t)G * K;
-  for (uint64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+  // only_ragged: just the G items of the last chunk (launched with G blocks)
+  const uint64_t first = only_ragged ? (uint64_t)blockIdx.x * K + (K - 1) : blockIdx.x;
+  const uint64_t step = only_ragged ? nitems : gridDim.x;
+  for (uint64_t item = first; item < nitems; item += step) {
     const int g = (int)(item / K);
     const uint64_t c = item - (uint64_t)g * K;
     const uint8_t* in_c = in + c * (uint64_t)chunk;
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
+    if (only_ragged && chunk_len % (64u * G) == 0) continue;  // k_encode_write_warp takes those
     const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;
     const uint32_t plen = plane_len(chunk_len, G, g);
     uint8_t* dest = out + item_off[item];
@@ -603,6 +608,276 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_write(const uint8_t* __r
         }
       }
       __syncthreads();
+    }
+  }
+}
+
+// =====================================================================================
+// pass B, regular chunks (chunk_len % (64*G) == 0): one CTA of 4 warps per chunk, warp s owns
+// the s-th quarter of every byte plane -- exactly one huff0 bitstream of each coded plane
+// (huf_compress.c:552-603) and a contiguous quarter of each raw plane.  The chunk is read
+// once (128-bit loads, the next tile prefetched), split in registers, and every plane is
+// finished by the same warp: no block-wide synchronisation after the per-chunk setup.
+//   coded plane: 16 symbols per lane -> 4 runs of <= 44 bits, warp suffix scan of the bit
+//                lengths (the last symbol is emitted first, huf_compress.c:474-499), OR into a
+//                warp-private bit buffer whose words are aligned with the destination's
+//                32-bit words, coalesced flush of the completed words;
+//   raw plane  : 512 bytes staged in shared memory, written with aligned 128-bit stores
+//                (funnel-shifted to the destination's alignment), byte stores at the edges.
+// =====================================================================================
+constexpr int kWbWarps = 4;
+constexpr uint32_t kWbTile = 512;                          // plane bytes per warp step (16 per lane)
+constexpr uint32_t kWbBitWords = (kWbTile * 11) / 32 + 4;  // worst-case tile bits + carry
+
+struct WbItem {
+  uint8_t* dest;
+  uint32_t size;
+  uint32_t hsize;
+  uint32_t sbytes[4];
+  uint32_t lg;
+  uint32_t type;  // 0 raw, 1 coded (size 1 = RLE)
+};
+
+template <int G>
+struct WbSmem {
+  WbItem item[G];
+  uint32_t code[G][256];                       // val | nb << 16
+  __align__(16) uint8_t nb[G][256];
+  uint32_t bitbuf[kWbWarps][G][kWbBitWords];
+  __align__(16) uint8_t stage[kWbWarps][kWbTile + 32];
+};
+
+// Per-stream bit writer state kept in registers by every lane of the warp (uniform values).
+struct WbStream {
+  uint8_t* gaddr;    // first byte of the bitstream in the output
+  uint32_t a;        // gaddr & 3
+  uint32_t B;        // bits placed so far, counted from the aligned word below gaddr
+  uint32_t flushed;  // whole words already written
+};
+
+__device__ __forceinline__ void wb_flush(uint32_t* bitbuf, WbStream& st, int lane) {
+  uint32_t* gword = reinterpret_cast<uint32_t*>(st.gaddr - st.a);
+  const uint32_t complete = (st.B >> 5) - st.flushed;
+  for (uint32_t w = lane; w < complete; w += 32) {
+    const uint32_t val = bitbuf[w];
+    if (st.flushed + w == 0 && st.a != 0) {
+      for (uint32_t bb = st.a; bb < 4; bb++) st.gaddr[bb - st.a] = (uint8_t)(val >> (8 * bb));
+    } else {
+      gword[st.flushed + w] = val;
+    }
+  }
+  const uint32_t carry = bitbuf[complete];
+  __syncwarp();
+  for (uint32_t w = lane; w <= complete; w += 32) bitbuf[w] = 0;
+  __syncwarp();
+  if (lane == 0) bitbuf[0] = carry;
+  st.flushed += complete;
+  __syncwarp();
+}
+
+template <int G>
+__global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk,
+                                                                     uint64_t K, int bits_mode, const uint8_t* __restrict__ types,
+                                                                     const uint32_t* __restrict__ sizes,
+                                                                     const EncSave* __restrict__ saves,
+                                                                     const uint64_t* __restrict__ item_off, uint8_t* out) {
+  __shared__ WbSmem<G> S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint64_t c = blockIdx.x; c < K; c += gridDim.x) {
+    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
+    if (chunk_len % (64u * G) != 0) continue;  // ragged tail: k_encode_write
+    const uint8_t* in_c = in + c * (uint64_t)chunk;
+    const uint32_t plen = chunk_len / G;
+    const uint32_t seg = plen >> 2;
+    const bool rot = (bits_mode == 1 && G > 1);
+    __syncthreads();
+    // ---- per-chunk setup: warp g prepares group g ----
+    if (warp < G) {
+      const int g = warp;
+      const uint64_t item = (uint64_t)g * K + c;
+      WbItem it;
+      it.dest = out + item_off[item];
+      it.type = types[item];
+      it.size = sizes[item];
+      it.hsize = 0;
+      it.lg = 0;
+      it.sbytes[0] = it.sbytes[1] = it.sbytes[2] = it.sbytes[3] = 0;
+      if (it.type == 1 && it.size == 1) {
+        if (lane == 0) it.dest[0] = saves[item].hdr[0];
+      } else if (it.type == 1) {
+        const EncSave* sv = saves + item;
+        it.hsize = sv->hsize;
+        it.lg = sv->lg;
+#pragma unroll
+        for (int q = 0; q < 4; q++) it.sbytes[q] = sv->sbytes[q];
+        reinterpret_cast<uint2*>(S.nb[g])[lane] = reinterpret_cast<const uint2*>(sv->nb)[lane];
+        __syncwarp();
+        warp_build_codes(S.nb[g], (int)it.lg, S.code[g]);
+        for (uint32_t i = lane; i < it.hsize; i += 32) it.dest[i] = sv->hdr[i];
+        if (lane < 3) {
+          it.dest[it.hsize + 2 * lane] = (uint8_t)it.sbytes[lane];
+          it.dest[it.hsize + 2 * lane + 1] = (uint8_t)(it.sbytes[lane] >> 8);
+        }
+      }
+      if (lane == 0) S.item[g] = it;
+    }
+    __syncthreads();
+
+    // ---- warp `warp` = stream index ----
+    const int s = warp;
+    WbStream st[G];
+    uint32_t raw_shift[G];  // destination misalignment of the raw plane quarter (bytes, mod 16)
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const WbItem& it = S.item[g];
+      st[g].gaddr = it.dest;
+      st[g].a = st[g].B = st[g].flushed = 0;
+      raw_shift[g] = 0;
+      if (it.type == 1 && it.size > 1) {
+        uint32_t at = it.hsize + 6;
+        for (int q = 0; q < s; q++) at += it.sbytes[q];
+        st[g].gaddr = it.dest + at;
+        st[g].a = (uint32_t)((uintptr_t)st[g].gaddr & 3);
+        st[g].B = 8 * st[g].a;
+        for (uint32_t w = lane; w < kWbBitWords; w += 32) S.bitbuf[warp][g][w] = 0;
+      } else if (it.type == 0) {
+        st[g].gaddr = it.dest + (uint64_t)s * seg;
+        raw_shift[g] = (uint32_t)((uintptr_t)st[g].gaddr & 15);
+      }
+    }
+    __syncwarp();
+
+    const uint8_t* src_s = in_c + (uint64_t)s * seg * G;
+    const uint32_t ntiles = (seg + kWbTile - 1) / kWbTile;
+    uint4 cur[G], nxt[G];
+    {
+      const uint32_t t0 = (ntiles - 1) * kWbTile;
+      if (t0 + 16 * lane < seg) {
+        const uint4* p = reinterpret_cast<const uint4*>(src_s + (uint64_t)(t0 + 16 * lane) * G);
+#pragma unroll
+        for (int i = 0; i < G; i++) nxt[i] = __ldg(p + i);
+      }
+    }
+    for (uint32_t ti = ntiles; ti-- > 0;) {
+      const uint32_t t0 = ti * kWbTile;
+      const uint32_t cnt = min(kWbTile, seg - t0);  // multiple of 16
+      const bool have = 16u * lane < cnt;
+#pragma unroll
+      for (int i = 0; i < G; i++) cur[i] = nxt[i];
+      if (ti > 0) {  // prefetch the next (lower) tile, always full
+        const uint4* p = reinterpret_cast<const uint4*>(src_s + (uint64_t)(t0 - kWbTile + 16 * lane) * G);
+#pragma unroll
+        for (int i = 0; i < G; i++) nxt[i] = __ldg(p + i);
+      }
+      uint4 pv[G];
+      if (have) {
+        uint32_t w[4 * G];
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+          w[4 * i] = cur[i].x; w[4 * i + 1] = cur[i].y; w[4 * i + 2] = cur[i].z; w[4 * i + 3] = cur[i].w;
+        }
+        if (rot) {
+#pragma unroll
+          for (int i = 0; i < 4 * G; i++) w[i] = rot_word<G>(w[i]);
+        }
+        split16<G>(w, pv);
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const uint32_t type = S.item[g].type, size = S.item[g].size;
+        if (type == 0) {
+          // ---- raw plane: 16 bytes per lane -> dest + t0 .. ----
+          uint8_t* stg = S.stage[warp];
+          if (have) *reinterpret_cast<uint4*>(stg + 16 * lane) = pv[g];
+          __syncwarp();
+          uint8_t* D = st[g].gaddr + t0;
+          const uint32_t m = raw_shift[g];
+          if (m == 0) {
+            if (have) *reinterpret_cast<uint4*>(D + 16 * lane) = pv[g];
+          } else {
+            const uint32_t head = 16 - m;  // bytes before the first aligned destination block
+            const uint32_t nblk = (cnt - head) >> 4;
+            if ((uint32_t)lane < nblk) {
+              const uint4 a4 = *reinterpret_cast<const uint4*>(stg + 16 * lane);
+              const uint4 b4 = *reinterpret_cast<const uint4*>(stg + 16 * lane + 16);
+              const uint32_t wv[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+              const uint32_t bs = (head & 3) * 8;
+              uint32_t t[7];
+#pragma unroll
+              for (int i = 0; i < 7; i++) t[i] = __funnelshift_r(wv[i], wv[i + 1], bs);
+              const bool s4 = head & 4, s8 = head & 8;
+              uint32_t u[5], o[4];
+#pragma unroll
+              for (int i = 0; i < 5; i++) u[i] = s8 ? t[i + 2] : t[i];
+#pragma unroll
+              for (int i = 0; i < 4; i++) o[i] = s4 ? u[i + 1] : u[i];
+              *reinterpret_cast<uint4*>(D + head + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            if ((uint32_t)lane < head) D[lane] = stg[lane];
+            const uint32_t done = head + 16 * nblk;
+            if ((uint32_t)lane < cnt - done) D[done + lane] = stg[done + lane];
+          }
+          __syncwarp();
+        } else if (size > 1) {
+          // ---- coded plane: this lane's 16 symbols, last byte first ----
+          const uint32_t* code = S.code[g];
+          uint64_t v[4] = {0, 0, 0, 0};
+          uint32_t l[4] = {0, 0, 0, 0};
+          if (have) {
+            const uint32_t wv[4] = {pv[g].x, pv[g].y, pv[g].z, pv[g].w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              const uint32_t sym = (wv[(15 - k) >> 2] >> (8 * ((15 - k) & 3))) & 0xFFu;
+              const uint32_t cd = code[sym];
+              v[k >> 2] |= (uint64_t)(cd & 0xFFFFu) << l[k >> 2];
+              l[k >> 2] += cd >> 16;
+            }
+          }
+          const uint32_t mine = l[0] + l[1] + l[2] + l[3];
+          uint32_t x = mine;  // suffix sum over lanes: lane 31 is emitted first
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_down_sync(0xffffffffu, x, o);
+            if (lane + o < 32) x += y;
+          }
+          const uint32_t tile_bits = __shfl_sync(0xffffffffu, x, 0);
+          uint32_t* bitbuf = S.bitbuf[warp][g];
+          uint32_t off = (st[g].B - 32 * st[g].flushed) + (x - mine);
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            if (l[r]) {
+              const uint32_t sh = off & 31, wi = off >> 5;
+              const uint32_t lo32 = (uint32_t)v[r], hi32 = (uint32_t)(v[r] >> 32);
+              const uint32_t w0 = lo32 << sh;
+              const uint32_t w1 = __funnelshift_l(lo32, hi32, sh);
+              const uint32_t w2 = sh ? (hi32 >> (32 - sh)) : 0u;
+              if (w0) atomicOr(&bitbuf[wi], w0);
+              if (w1) atomicOr(&bitbuf[wi + 1], w1);
+              if (w2) atomicOr(&bitbuf[wi + 2], w2);
+              off += l[r];
+            }
+          }
+          __syncwarp();
+          st[g].B += tile_bits;
+          wb_flush(bitbuf, st[g], lane);
+        }
+      }
+    }
+    // ---- end marks and the last partial bytes of every bitstream ----
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (S.item[g].type == 1 && S.item[g].size > 1) {
+        uint32_t* bitbuf = S.bitbuf[warp][g];
+        if (lane == 0) bitbuf[(st[g].B - 32 * st[g].flushed) >> 5] |= 1u << (st[g].B & 31);
+        __syncwarp();
+        const uint32_t first_byte = max(4 * st[g].flushed, st[g].a);
+        const uint32_t end_byte = st[g].a + S.item[g].sbytes[s];
+        for (uint32_t bb = first_byte + lane; bb < end_byte; bb += 32) {
+          const uint32_t rel = bb - 4 * st[g].flushed;
+          st[g].gaddr[bb - st[g].a] = (uint8_t)(bitbuf[rel >> 2] >> (8 * (rel & 3)));
+        }
+        __syncwarp();
+      }
     }
   }
 }

@@ -43,10 +43,10 @@ inline bool cuda_ok(cudaError_t e) {
 // ---- optional per-kernel timing (CUDA events on the launching stream) ----------------
 // Off by default.  bench.py turns it on to attribute the step time to kernels; the events
 // sit between launches on the same stream, so they do not change the schedule.
-enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKHufDecodePlanar, kKRegroup, kKEncodeStats, kKEncodeTable, kKEncodeScan, kKEncodeWrite, kKSplit,
+enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKHufDecodePlanar, kKRegroup, kKEncodeStats, kKEncodeTable, kKEncodeScan, kKEncodeWrite, kKEncodeWriteRagged, kKSplit,
                 kKRegroupPlanar, kKCount };
 const char* const kKernelNames[kKCount] = {"k_decode_meta", "k_huf_decode_fused", "k_huf_decode_planar", "k_regroup", "k_encode_hist", "k_encode_table",
-                                           "k_encode_scan", "k_encode_write", "k_split_planar", "k_regroup_planar"};
+                                           "k_encode_scan", "k_encode_write_warp", "k_encode_write_ragged", "k_split_planar", "k_regroup_planar"};
 struct TimedSpan {
   int id;
   cudaEvent_t a, b;
