@@ -1,0 +1,108 @@
+"""The safetensors load path (SURVEY section 8 '* surface only', 8f N1): SafeOpen, the
+zipnn_safetensors() patch, and the .znn.safetensors writer/reader.  Mirrors the reference's own
+safetensors test (tests/simple_stress_tests.py:215-263) and adds interoperability with a file
+written by the reference script (tests/golden/ref_model.znn.safetensors)."""
+import json
+import os
+
+import pytest
+import torch
+from safetensors import safe_open
+from safetensors.torch import save_file
+
+from golden_inputs import raw_bytes
+from golden_safetensors_inputs import make_checkpoint
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "ref_model.znn.safetensors")
+
+
+def _same(a, b):
+    return a.dtype == b.dtype and tuple(a.shape) == tuple(b.shape) and raw_bytes(a.cpu()) == raw_bytes(b.cpu())
+
+
+def test_metadata_helpers_cpu():
+    from zipnn_b200.util_safetensors import (build_compressed_tensor_info, get_compressed_tensors_metadata,
+                                             set_compressed_tensors_metadata)
+    t = torch.zeros(3, 5, dtype=torch.bfloat16)
+    info = build_compressed_tensor_info(t)
+    assert info == {"dtype": "bfloat16", "shape": "[3, 5]"}
+    meta = {"format": "pt"}
+    set_compressed_tensors_metadata({"w": info}, meta)
+    assert json.loads(meta["znn_compressed_vectors"]) == {"w": info}
+    assert get_compressed_tensors_metadata(meta) == {"w": info}
+    assert get_compressed_tensors_metadata(None) == {}
+    with safe_open(GOLD, "pt", "cpu") as f:  # what the reference wrote
+        names = set(get_compressed_tensors_metadata(f.metadata()))
+    assert names == {"w_bf16", "w_fp16", "w_fp32", "w_fp8", "big_bf16"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device", ["cpu", "cuda"])
+def test_reads_file_written_by_the_reference(device):
+    from zipnn_b200 import SafeOpen
+    want = make_checkpoint()
+    with SafeOpen(GOLD, "pt", device) as f:
+        assert set(f.keys()) == set(want)
+        for name in f.keys():
+            got = f.get_tensor(name)
+            assert got.device.type == device
+            assert _same(got, want[name]), name
+        assert f.get_slice("w_bf16") is NotImplementedError  # as the reference
+        assert f.get_slice("ids")[2:4].shape == (2, 100)
+
+
+@pytest.mark.gpu
+def test_writer_output_is_the_reference_file(tmp_path):
+    """Our writer on the same checkpoint produces the same compressed entries, byte for byte."""
+    from zipnn_b200 import compress_safetensors_file, decompress_safetensors_file
+    src = tmp_path / "m.safetensors"
+    save_file(make_checkpoint(), str(src), {"format": "pt"})
+    path, clen, olen = compress_safetensors_file(str(src))
+    assert path.endswith(".znn.safetensors") and clen < olen
+    with safe_open(path, "pt", "cpu") as ours, safe_open(GOLD, "pt", "cpu") as ref:
+        assert set(ours.keys()) == set(ref.keys())
+        assert json.loads(ours.metadata()["znn_compressed_vectors"]) == json.loads(ref.metadata()["znn_compressed_vectors"])
+        for name in ref.keys():
+            assert torch.equal(ours.get_tensor(name), ref.get_tensor(name)), name
+    back = decompress_safetensors_file(path)
+    with safe_open(back, "pt", "cpu") as f:
+        for name, t in make_checkpoint().items():
+            assert _same(f.get_tensor(name), t), name
+
+
+@pytest.mark.gpu
+def test_patch_is_what_a_loader_sees(tmp_path):
+    """vLLM's weight iterator does `from safetensors.torch import safe_open` after the patch and
+    then `with safe_open(file, framework="pt") as f: for name in f.keys(): f.get_tensor(name)`."""
+    import safetensors.torch
+    from zipnn_b200 import SafeOpen, compress_safetensors_file, zipnn_safetensors
+    src = tmp_path / "m.safetensors"
+    want = make_checkpoint()
+    save_file(want, str(src))          # no metadata dict in the source file
+    path, _, _ = compress_safetensors_file(str(src))
+    saved = safetensors.torch.safe_open
+    try:
+        zipnn_safetensors()
+        assert safetensors.torch.safe_open is SafeOpen
+        with safetensors.torch.safe_open(path, framework="pt") as f:
+            for name in f.keys():
+                assert _same(f.get_tensor(name), want[name]), name
+    finally:
+        safetensors.torch.safe_open = saved
+
+
+@pytest.mark.gpu
+def test_tiny_tensors_survive_the_raw_fallback(tmp_path):
+    """The reference stores its in-place-rotated copy when a tensor does not compress and so
+    corrupts tiny bf16/fp32 tensors; we store the original bytes."""
+    from zipnn_b200 import SafeOpen, compress_safetensors_file
+    tensors = {"tiny": torch.tensor([1.5, -2.25, 3.0, 0.1, 7.0, -0.5, 9.0, 1e-3], dtype=torch.bfloat16),
+               "big": (torch.randn(4096) * 0.02).to(torch.bfloat16), "one": torch.tensor([3.25], dtype=torch.float32)}
+    src = tmp_path / "t.safetensors"
+    save_file(tensors, str(src))
+    path, _, _ = compress_safetensors_file(str(src))
+    with SafeOpen(path, "pt", "cpu") as f:
+        assert "tiny" not in f.compressed_tensors_metadata and "big" in f.compressed_tensors_metadata
+        for name, t in tensors.items():
+            assert _same(f.get_tensor(name), t), name
