@@ -410,6 +410,7 @@ __device__ __forceinline__ void tile_to_global(const uint8_t* tile, uint8_t* dst
 }
 
 // Canonical code values from lengths, one warp (huf_compress.c:390-407).
+template <bool kValHigh>
 __device__ __forceinline__ void warp_build_codes(const uint8_t* nb, int lg, uint32_t* code) {
   const int lane = threadIdx.x & 31;
   uint32_t per_len[kHufLogMax + 1];
@@ -442,7 +443,7 @@ __device__ __forceinline__ void warp_build_codes(const uint8_t* nb, int lg, uint
       if (mine == l) val = start[l] + __popc(m & ((1u << lane) - 1u));
       start[l] += __popc(m);
     }
-    code[base + lane] = val | ((uint32_t)mine << 16);
+    code[base + lane] = kValHigh ? ((val << 8) | (uint32_t)mine) : (val | ((uint32_t)mine << 16));
   }
 }
 
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_write(const uint8_t* __r
     }
     __syncthreads();
     const uint32_t hsize = S.save.hsize;
-    if (warp == 0) warp_build_codes(S.save.nb, (int)S.save.lg, S.code);
+    if (warp == 0) warp_build_codes<false>(S.save.nb, (int)S.save.lg, S.code);
     if (warp == 1) {
       for (uint32_t i = lane; i < hsize; i += 32) dest[i] = S.save.hdr[i];
       if (lane < 3) {
@@ -640,8 +641,8 @@ struct WbItem {
 
 template <int G>
 struct WbSmem {
+  uint32_t code[G][256];                       // val << 8 | nb
   WbItem item[G];
-  uint32_t code[G][256];                       // val | nb << 16
   __align__(16) uint8_t nb[G][256];
   uint32_t bitbuf[kWbWarps][G][kWbBitWords];
   __align__(16) uint8_t stage[kWbWarps][kWbTile + 32];
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
         for (int q = 0; q < 4; q++) it.sbytes[q] = sv->sbytes[q];
         reinterpret_cast<uint2*>(S.nb[g])[lane] = reinterpret_cast<const uint2*>(sv->nb)[lane];
         __syncwarp();
-        warp_build_codes(S.nb[g], (int)it.lg, S.code[g]);
+        warp_build_codes<true>(S.nb[g], (int)it.lg, S.code[g]);
         for (uint32_t i = lane; i < it.hsize; i += 32) it.dest[i] = sv->hdr[i];
         if (lane < 3) {
           it.dest[it.hsize + 2 * lane] = (uint8_t)it.sbytes[lane];
@@ -820,17 +821,27 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
           __syncwarp();
         } else if (size > 1) {
           // ---- coded plane: this lane's 16 symbols, last byte first ----
-          const uint32_t* code = S.code[g];
+          // Run r = symbols 4r..4r+3 = bytes 3,2,1,0 of word 3-r.  Table entries are val << 8 | nb;
+          // the byte is turned into the table's byte offset with one shift + one mask, two codes are
+          // joined in 32 bits (<= 22), two pairs in 64 (<= 44).
+          const unsigned char* code = reinterpret_cast<const unsigned char*>(S.code[g]);
           uint64_t v[4] = {0, 0, 0, 0};
           uint32_t l[4] = {0, 0, 0, 0};
           if (have) {
             const uint32_t wv[4] = {pv[g].x, pv[g].y, pv[g].z, pv[g].w};
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-              const uint32_t sym = (wv[(15 - k) >> 2] >> (8 * ((15 - k) & 3))) & 0xFFu;
-              const uint32_t cd = code[sym];
-              v[k >> 2] |= (uint64_t)(cd & 0xFFFFu) << l[k >> 2];
-              l[k >> 2] += cd >> 16;
+            for (int r = 0; r < 4; r++) {
+              const uint32_t w = wv[3 - r];
+              const uint32_t e3 = *reinterpret_cast<const uint32_t*>(code + ((w >> 22) & 0x3FCu));
+              const uint32_t e2 = *reinterpret_cast<const uint32_t*>(code + ((w >> 14) & 0x3FCu));
+              const uint32_t e1 = *reinterpret_cast<const uint32_t*>(code + ((w >> 6) & 0x3FCu));
+              const uint32_t e0 = *reinterpret_cast<const uint32_t*>(code + ((w << 2) & 0x3FCu));
+              const uint32_t n3 = e3 & 0xFFu, n2 = e2 & 0xFFu, n1 = e1 & 0xFFu, n0 = e0 & 0xFFu;
+              const uint32_t hi = (e3 >> 8) | ((e2 >> 8) << n3);  // emitted first
+              const uint32_t lo = (e1 >> 8) | ((e0 >> 8) << n1);
+              const uint32_t lh = n3 + n2;
+              v[r] = (uint64_t)hi | ((uint64_t)lo << lh);
+              l[r] = lh + n1 + n0;
             }
           }
           const uint32_t mine = l[0] + l[1] + l[2] + l[3];
