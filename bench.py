@@ -329,7 +329,6 @@ def run_ours(args, rank, local_rank, world):
         "k_encode_hist": N,                     # reads every input byte once
         "k_encode_write_warp": N + Cb,               # reads the input again, writes the stream
         "k_huf_decode_fused": Cb + N,           # reads the whole stream, writes the elements (fused decode + regroup)
-        "k_huf_decode_pair": Cb + N,            # same traffic, pair-table variant (bf16 / fp32)
     }
     dom_ms = per_launch[dom][0]
     achieved = algo.get(dom, N) / (dom_ms * 1e-3) / 1e9

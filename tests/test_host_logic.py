@@ -86,7 +86,6 @@ def _emu():
     E = C.CDLL(so)
     E.emu_table_from_counts.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     E.emu_read_weights.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
-    E.emu_pair_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
     return E
 
 
@@ -151,63 +150,3 @@ def test_device_weight_parser_rejects_garbage():
         r = E.emu_read_weights(buf.ctypes.data, n, w.ctypes.data, C.byref(ns), C.byref(lg))
         assert r == -1 or (0 < r <= n and 1 <= lg.value <= 12 and 2 <= ns.value <= 256)
 
-
-def test_pair_decode_table_matches_oracle():
-    """The pair table of k_huf_decode_pair (huf_serial.cuh: huf_fill_pair_table) and its step rule,
-    modelled on the host, decode every stream of oracle-made huff0 blocks back to the input; on
-    exponent-like planes a table step yields close to two symbols."""
-    E = _emu()
-    rng = np.random.default_rng(11)
-    decoded = demoted = 0
-    best = 9.0
-    for it in range(240):
-        kind = it % 6
-        size = int(rng.choice([64, 300, 2048, 32768, 131072, int(rng.integers(40, 131073))]))
-        if kind == 0:
-            x = (rng.standard_normal(size) * 0.02).astype(np.float32)
-            src = (x.view(np.uint32) >> 23).astype(np.uint8)
-        elif kind == 1:
-            k = int(rng.integers(2, 12))
-            src = rng.choice(k, size, p=rng.dirichlet(np.ones(k) * rng.uniform(0.05, 2))).astype(np.uint8)
-        elif kind == 2:
-            k = int(rng.integers(2, 256))
-            src = rng.choice(k, size, p=rng.dirichlet(np.ones(k) * rng.uniform(0.01, 1))).astype(np.uint8)
-        elif kind == 3:
-            src = np.minimum(rng.geometric(rng.uniform(0.02, 0.9), size), 255).astype(np.uint8)
-        elif kind == 4:
-            src = (rng.standard_normal(size) * rng.uniform(0.5, 40) + 128).clip(0, 255).astype(np.uint8)
-        else:
-            src = (255 - np.minimum(rng.zipf(rng.uniform(1.1, 3), size), 255)).astype(np.uint8)
-        r, blk = O.huf_compress(src)
-        if r <= 1 or r >= size:
-            continue
-        buf = np.concatenate([np.frombuffer(blk, np.uint8), np.zeros(8, np.uint8)])
-        w = np.zeros(256, np.uint8)
-        ns, lg = C.c_int(0), C.c_int(0)
-        h = E.emu_read_weights(buf.ctypes.data, r, w.ctypes.data, C.byref(ns), C.byref(lg))
-        assert h > 0
-        body = buf[h:r]
-        l = [int(body[0]) | int(body[1]) << 8, int(body[2]) | int(body[3]) << 8, int(body[4]) | int(body[5]) << 8]
-        l.append(body.size - 6 - sum(l))
-        seg = (size + 3) // 4
-        off, at, steps_all = 6, 0, 0
-        for j in range(4):
-            n = min(seg, size - at)
-            st = np.ascontiguousarray(body[off: off + l[j]])
-            out = np.zeros(n + 2, np.uint8)
-            steps = C.c_uint32(0)
-            rc = E.emu_pair_decode(w.ctypes.data, ns.value, lg.value, st.ctypes.data, l[j], out.ctypes.data, n, C.byref(steps))
-            if rc == -1:
-                demoted += 1
-                break
-            assert rc == 0, (it, j, rc)
-            assert np.array_equal(out[:n], src[at: at + n]), (it, j)
-            off += l[j]
-            at += n
-            steps_all += steps.value
-        else:
-            decoded += 1
-            if kind == 0 and size >= 32768:
-                best = min(best, steps_all / size)
-    assert decoded > 150 and demoted < 60
-    assert best < 0.6       # ~0.51 table steps per symbol on a float exponent plane

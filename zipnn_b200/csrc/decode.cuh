@@ -175,14 +175,19 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// Bit window, CPU style (bitstream.h:272-443) on top of the ring: a 64-bit container holding
-// bytes [p, p+8) of the stream and a count `c` of bits already consumed from its top.  A symbol
-// costs: peek = (container << c) >> 53, consume = c += length.  Every 4 symbols (4 x 11 bits
-// + 7 <= 64 - 11) the container is re-read at byte granularity: p -= c >> 3, c &= 7.  No branch.
+// Bit window: a 64-bit container `cont` holding bytes [q, q+8) of the stream (q 4-aligned in the
+// ring's offset space) and a count `c` of bits already consumed from its top, as in
+// bitstream.h:272-443, but refilled one aligned 32-bit word at a time: when 32 or more bits are
+// gone, cont = cont << 32 | next, where `next` (the word below q) was read from the ring at the
+// PREVIOUS refill.  A symbol costs peek = (cont << c) >> 53 and c += length; the refill check runs
+// every 2 symbols (31 + 2 x 11 <= 64 - 11).  The shared-memory read is off the dependent chain
+// (its result is needed one refill later) and happens once per 32 stream bits instead of three
+// times per 4 symbols.
 struct BitWindow {
-  uint64_t cont;         // bytes [p, p+8) of the stream, little endian
+  uint64_t cont;         // bytes [q, q+8) of the stream, little endian
   uint32_t c;            // bits consumed from the top of `cont`
-  uint32_t p;            // byte offset (from gbase) of the container's lowest byte; moves down
+  uint32_t q;            // byte offset (from gbase) of the container's lowest byte; moves down by 4
+  uint32_t next;         // the word at q - 4
   uint32_t fetch;        // byte offset (from gbase) of the lowest 16-byte block already requested
   uint32_t start_bit;    // bit offset (from gbase) of the first stream bit (exact-consumption check)
   const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
@@ -199,28 +204,22 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
 #pragma unroll 2
   for (int i = 0; i < maxn; i++) {
     const uint32_t f = b.fetch - 16;
-    // block [f, f+16) replaces ring bytes [f+128, f+144): allowed once they lie above the
-    // aligned words a reload of the container can still touch, (p & ~3) + 12
-    if (b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.p + 12) {
+    // block [f, f+16) replaces ring bytes [f+128, f+144): free once they lie at or above q
+    // (the container and `next` are in registers; later reads are at q - 8 and below)
+    if (b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.q) {
       cp_async16(const_cast<uint8_t*>(b.ring) + (f & (kRingBytes - 1)), b.gbase + f);
       b.fetch = f;
     }
   }
 }
 
-// Container := bytes [p, p+8) from the ring (three aligned words, funnel-shifted).
-__device__ __forceinline__ void window_load(BitWindow& b) {
-  const uint32_t a = b.p & ~3u;
-  const uint32_t w0 = ring_word(b.ring, a), w1 = ring_word(b.ring, a + 4), w2 = ring_word(b.ring, a + 8);
-  const uint32_t sh = (b.p & 3u) * 8;
-  const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-  b.cont = ((uint64_t)hi << 32) | lo;
-}
-
-__device__ __forceinline__ void window_reload(BitWindow& b) {
-  b.p -= b.c >> 3;
-  b.c &= 7u;
-  window_load(b);
+__device__ __forceinline__ void window_refill(BitWindow& b) {
+  if (b.c >= 32u) {
+    b.cont = (b.cont << 32) | b.next;
+    b.c -= 32u;
+    b.q -= 4u;
+    b.next = ring_word(b.ring, b.q - 4u);
+  }
 }
 
 // s points at the stream (len bytes); `lo` is the first readable byte of the buffer.
@@ -236,18 +235,19 @@ __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint
   b.start_bit = 8u * s_off;
   if (mark == b.start_bit) return false;
   const uint32_t top_byte = (mark - 1) >> 3;
-  b.p = top_byte - 7;
-  b.c = 8u * (top_byte + 1) - mark;  // 0..7 bits above the first unread bit
+  b.q = (top_byte & ~3u) - 4u;
+  b.c = 8u * (b.q + 8u) - mark;  // 1..32 bits above the first unread bit
   b.fetch = (top_byte & ~15u) + 16;
   ring_top_up(b, (int)(kRingBytes / 16));
   cp_async_commit();
   cp_async_wait<0>();
-  window_load(b);
+  b.cont = ((uint64_t)ring_word(ring, b.q + 4u) << 32) | ring_word(ring, b.q);
+  b.next = ring_word(ring, b.q - 4u);
   return true;
 }
 
 __device__ __forceinline__ bool window_exact(const BitWindow& b) {
-  return 8u * (b.p + 8) - b.c == b.start_bit;  // every bit down to the stream start consumed, none below
+  return 8u * (b.q + 8u) - b.c == b.start_bit;  // every bit down to the stream start consumed, none below
 }
 
 // ---- decode tables ------------------------------------------------------------------
@@ -290,8 +290,9 @@ __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t 
   cp_async_commit();
 #pragma unroll
   for (int q = 0; q < 4; q++) {
-    window_reload(b);
+    window_refill(b);
     const uint32_t e0 = window_decode(b, lut), e1 = window_decode(b, lut);
+    window_refill(b);
     const uint32_t e2 = window_decode(b, lut), e3 = window_decode(b, lut);
     o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
   }
@@ -302,7 +303,7 @@ template <class LUT>
 __device__ __forceinline__ uint32_t decode1(BitWindow& b, const LUT& lut) {
   ring_top_up(b, 1);
   cp_async_commit();
-  window_reload(b);
+  window_refill(b);
   const uint32_t s = window_decode(b, lut) & 0xFFu;
   cp_async_wait<0>();
   return s;
@@ -751,297 +752,6 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     __syncwarp();
   }
   if (live && !window_exact(b)) atomicOr(&cfg.ctrl->error, kErrCorrupt);
-}
-
-// ====================================================================================
-// Kernel 2c: fused mode with a PAIR table, for planes whose codes are short (the exponent
-// plane of bf16 / fp32: 2.6 bits per symbol, 97 % of adjacent code pairs fit in 8 bits).
-//
-// The cost of this decoder is the serial chain peek -> table -> length -> next peek, once per
-// symbol.  Here a primary entry decodes TWO symbols whenever both codes fit in the 8-bit index
-// and both symbols belong to the 8 symbols with the shortest codes, so the chain runs about
-// once per 1.9 symbols.  The entry stays 16 bits (same 512 B per chunk):
-//     0                                  -> first code longer than 8 bits: tail table
-//     [3:0] len  [11:4] symbol           -> one symbol
-//     [15]=1 [3:0] len0+len1 [6:4] i0 [10:8] i1 -> two symbols, indices into the shortlist
-// The shortlist lives in two registers and is expanded with one PRMT; the chain only needs the
-// low 4 bits.  Symbols are collected in a byte queue and written 4 at a time into the upper
-// part of the lane's output row; once every lane of the warp has its 128/G symbols the row is
-// merged with the other planes exactly as in k_huf_decode_fused.
-// ====================================================================================
-struct PairSmem {
-  uint16_t prim[kDecItemsPerWarp][256];
-  uint16_t tail[kDecItemsPerWarp][kTailEntries];   // also scratch for the table parse
-  __align__(16) uint8_t ring[32][kRingBytes];      // weights[8][256] alias it during the parse
-  __align__(16) uint8_t stage[32][128];            // output rows; single-symbol tables during the build
-  uint32_t shortlist[kDecItemsPerWarp][4];         // 8 symbols (2 words), their code lengths (1 word), pad
-};
-
-struct PairLut {
-  const uint16_t* prim;
-  const uint16_t* tail;
-  uint32_t x_long;  // unused on the fast path (a zero entry means tail)
-  uint32_t sl_lo, sl_hi, sl_len;
-};
-
-struct SymQueue {
-  uint64_t q;      // decoded symbols not yet written, lowest byte first
-  uint32_t qn;     // how many
-  uint32_t total;  // symbols decoded so far in this stream
-};
-
-// One chain step: 1 or 2 symbols into the queue.  `limit` = symbols in the stream.
-__device__ __forceinline__ void pair_step(BitWindow& b, const PairLut& lut, SymQueue& sq, uint32_t limit) {
-  const uint32_t top32 = (uint32_t)((b.cont << b.c) >> 32);
-  uint32_t e = lut.prim[top32 >> 24];
-  uint32_t len = e & 15u;
-  if (len == 0) {  // code longer than 8 bits
-    const uint32_t et = lut.tail[top32 >> 21];
-    len = et >> 8;
-    e = (et & 0xFFu) << 4;
-  }
-  const bool is_pair = (e & 0x8000u) != 0;
-  const bool take2 = is_pair && (sq.total + 2 <= limit);
-  const uint32_t both = __byte_perm(lut.sl_lo, lut.sl_hi, (e >> 4) & 0x77u) & 0xFFFFu;
-  if (is_pair && !take2) len = (lut.sl_len >> (4 * ((e >> 4) & 7u))) & 15u;  // last symbol of the stream
-  const uint32_t syms = is_pair ? (take2 ? both : (both & 0xFFu)) : ((e >> 4) & 0xFFu);
-  const uint32_t n = take2 ? 2u : 1u;
-  b.c += len;
-  sq.q |= (uint64_t)syms << (8 * sq.qn);
-  sq.qn += n;
-  sq.total += n;
-}
-
-template <int G>
-__global__ void __launch_bounds__(32) k_huf_decode_pair(DecodeCfg cfg, uint8_t* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  PairSmem& S = *reinterpret_cast<PairSmem*>(smem_raw);
-  const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
-  const uint64_t K = cfg.K;
-  const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
-  const bool active = (c < K) && cfg.mode[c] == kModeFused;
-  if (__ballot_sync(0xffffffffu, active) == 0) return;
-
-  ItemDesc d;
-  d.kind = kRaw;
-  d.src_off = 0;
-  d.src_len = d.dec_len = 0;
-  if (active) d = cfg.items[(uint64_t)(G - 1) * K + c];
-
-  int lg = 0, hsize = -1, x_long = 0;
-  {
-    uint8_t* weights = &S.ring[0][0] + slot * 256;
-    if (active && stream == 0) {
-      int nsym = 0;
-      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tail[slot][0]);
-      hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
-      if (hsize >= 0) {
-        x_long = huf_fill_pair_table(S.prim[slot], S.tail[slot], reinterpret_cast<uint16_t*>(&S.stage[0][0]) + slot * 256,
-                                 S.shortlist[slot], weights, nsym, lg);
-        if (x_long < 0) hsize = -1;
-      }
-      if (hsize < 0) {  // hand the chunk to the general kernels (see k_huf_decode_fused)
-        const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
-        if (s >= cfg.max_slots) {
-          atomicOr(&cfg.ctrl->error, kErrWorkspace);
-          cfg.mode[c] = (uint8_t)kModeSkip;
-        } else {
-          cfg.slot[c] = s;
-          cfg.mode[c] = (uint8_t)kModeGeneral;
-        }
-      }
-    }
-    __syncwarp();
-    lg = __shfl_sync(0xffffffffu, lg, lane & ~3);
-    hsize = __shfl_sync(0xffffffffu, hsize, lane & ~3);
-    x_long = __shfl_sync(0xffffffffu, x_long, lane & ~3);
-    __syncwarp();
-  }
-  bool live = active && hsize >= 0;
-
-  const uint8_t* p = cfg.body + d.src_off + (live ? hsize : 0);
-  const uint32_t rest = live ? d.src_len - (uint32_t)hsize : 0;
-  uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-  if (live) {
-    bool ok = rest >= 10;
-    if (ok) {
-      l0 = p[0] | (p[1] << 8);
-      l1 = p[2] | (p[3] << 8);
-      l2 = p[4] | (p[5] << 8);
-      ok = l0 + l1 + l2 + 6 <= rest;
-      l3 = rest - (l0 + l1 + l2 + 6);
-      ok = ok && l0 && l1 && l2 && l3;
-    }
-    if (!ok) {
-      atomicOr(&cfg.ctrl->error, kErrCorrupt);
-      live = false;
-    }
-  }
-  const uint32_t seg = d.dec_len >> 2;
-  uint32_t s_off = 6, s_len = l0;
-  if (stream == 1) { s_off += l0; s_len = l1; }
-  if (stream == 2) { s_off += l0 + l1; s_len = l2; }
-  if (stream == 3) { s_off += l0 + l1 + l2; s_len = l3; }
-  const uint32_t out_off = (uint32_t)stream * seg;
-
-  constexpr int NS = (G > 1) ? G - 1 : 1;
-  constexpr int kIters = 8 / G;          // 16-symbol groups per 128-byte output row
-  constexpr uint32_t kRowSyms = 128 / G;  // symbols per row
-  struct RowSide {
-    const uint4* blk;
-    uint32_t shift, step;
-    uint4 cur;          // block holding the first byte of the row
-    uint4 nx[kIters];   // the following blocks
-  } side[NS];
-  const uint4* hi_block = reinterpret_cast<const uint4*>(((uintptr_t)(cfg.body + cfg.body_len) - 1) & ~(uintptr_t)15);
-  if (G > 1 && live) {
-#pragma unroll
-    for (int g = 0; g < G - 1; g++) {
-      const uint64_t i = (uint64_t)g * K + c;
-      const ItemDesc t = cfg.items[i];
-      const uint8_t* q;
-      if (t.kind == kRle) {
-        q = cfg.fill + i * kFillBytes;
-        side[g].step = 0;
-      } else {
-        q = cfg.body + t.src_off + out_off;
-        side[g].step = 1;
-      }
-      side[g].shift = (uint32_t)((uintptr_t)q & 15);
-      side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
-      side[g].cur = ldg128(side[g].blk);
-    }
-  }
-
-  const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  PairLut lut;
-  lut.prim = S.prim[slot];
-  lut.tail = S.tail[slot];
-  lut.x_long = (uint32_t)x_long;
-  lut.sl_lo = S.shortlist[slot][0];
-  lut.sl_hi = S.shortlist[slot][1];
-  lut.sl_len = S.shortlist[slot][2];
-  __syncwarp();  // the build scratch in `stage` is dead from here on
-  BitWindow b;
-  if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
-    atomicOr(&cfg.ctrl->error, kErrCorrupt);
-    live = false;
-  }
-
-  const uint32_t my_rows = live ? seg / kRowSyms : 0;
-  uint32_t max_rows = my_rows;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) max_rows = max(max_rows, __shfl_xor_sync(0xffffffffu, max_rows, o));
-  const uint64_t my_out = (uint64_t)(uintptr_t)(out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G);
-  uint64_t row_out[8];
-  uint32_t row_cnt[8];
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const int src = r * 4 + (lane >> 3);
-    row_out[r] = __shfl_sync(0xffffffffu, my_out, src) + (uint64_t)(lane & 7) * 16;
-    row_cnt[r] = __shfl_sync(0xffffffffu, my_rows, src);
-  }
-
-  SymQueue sq;
-  sq.q = 0;
-  sq.qn = 0;
-  sq.total = 0;
-  uint32_t written = 0;  // symbols already moved from the queue into rows
-  constexpr uint32_t kSymBase = 128 - kRowSyms;  // the symbols of a row wait in its upper bytes
-
-  for (uint32_t row = 0; row < max_rows; row++) {
-    if (row < my_rows) {
-      // ---- the other planes' blocks for this row (arrive while the symbols are decoded) ----
-      if (G > 1) {
-        const bool last = row + 1 >= my_rows;
-#pragma unroll
-        for (int g = 0; g < G - 1; g++)
-#pragma unroll
-          for (int k = 0; k < kIters; k++) {
-            const uint4* nb = side[g].blk + (k + 1) * side[g].step;
-            if (last && side[g].step && nb > hi_block) nb = hi_block;
-            side[g].nx[k] = ldg128(nb);
-          }
-      }
-      // ---- phase 1: decode until this lane holds the row's symbols ----
-      const uint32_t target = (row + 1) * kRowSyms;
-      while (sq.total < target) {
-        ring_top_up(b, 1);
-        cp_async_commit();
-        window_reload(b);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (sq.total < target) pair_step(b, lut, sq, seg);
-          if (sq.qn >= 4) {
-            const uint32_t off = kSymBase + (written % kRowSyms);
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(stage_unit(S.stage, lane, (int)(off >> 4))) + (off & 15)) =
-                (uint32_t)sq.q;
-            sq.q >>= 32;
-            sq.qn -= 4;
-            written += 4;
-          }
-        }
-        cp_async_wait<3>();  // a group has 4 trips (>= 16 symbols) to land; its bytes are needed ~18 trips later
-      }
-      // ---- phase 2: merge with the other planes, kIters groups of 16 symbols ----
-#pragma unroll
-      for (int k = 0; k < kIters; k++) {
-        uint32_t pl[G][4];
-        {
-          const uint32_t off = kSymBase + 16 * k;
-          const uint4 v = *stage_unit(S.stage, lane, (int)(off >> 4));
-          pl[G - 1][0] = v.x; pl[G - 1][1] = v.y; pl[G - 1][2] = v.z; pl[G - 1][3] = v.w;
-        }
-        if (G > 1) {
-#pragma unroll
-          for (int g = 0; g < G - 1; g++) take16(k == 0 ? side[g].cur : side[g].nx[(k + kIters - 1) % kIters], side[g].nx[k], side[g].shift, pl[g]);
-          if (rot) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) unrotate_planes(pl[(G - 2) % G][q], pl[G - 1][q]);
-          }
-          uint32_t w[4 * G];
-          if (G == 2) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              w[2 * q] = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140);
-              w[2 * q + 1] = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint32_t t0 = __byte_perm(pl[0][q], pl[1 % G][q], 0x5140), t1 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x5140);
-              const uint32_t t2 = __byte_perm(pl[0][q], pl[1 % G][q], 0x7362), t3 = __byte_perm(pl[2 % G][q], pl[3 % G][q], 0x7362);
-              w[4 * q] = __byte_perm(t0, t1, 0x5410);
-              w[4 * q + 1] = __byte_perm(t0, t1, 0x7632);
-              w[4 * q + 2] = __byte_perm(t2, t3, 0x5410);
-              w[4 * q + 3] = __byte_perm(t2, t3, 0x7632);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < G; q++)
-            *stage_unit(S.stage, lane, k * G + q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-        }
-      }
-      if (G > 1) {
-#pragma unroll
-        for (int g = 0; g < G - 1; g++) {
-          side[g].cur = side[g].nx[kIters - 1];
-          side[g].blk += kIters * side[g].step;
-        }
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int src = r * 4 + (lane >> 3);
-      if (row < row_cnt[r]) {
-        const uint4 v = *stage_unit(S.stage, src, lane & 7);
-        *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
-      }
-    }
-    __syncwarp();
-  }
-  if (live && !(window_exact(b) && sq.total == seg && sq.qn == 0)) atomicOr(&cfg.ctrl->error, kErrCorrupt);
 }
 
 // ====================================================================================

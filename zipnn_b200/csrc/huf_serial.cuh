@@ -757,98 +757,4 @@ ZB_HD inline int huf_read_weights(uint8_t* weights /*256*/, int* nsym, int* lg_o
   return (int)isize + 1;
 }
 
-// ------------------------------------------------------------------------------------------
-// Pair decode table (used by k_huf_decode_pair, see decode.cuh).  Index space = the next
-// kPairIndexBits bits of the stream; `prim` is indexed by the top 8 of them.
-//   prim entry 0                                   : code longer than 8 bits -> tail[index11] = symbol | len << 8
-//   prim entry [3:0] len [11:4] symbol             : one symbol
-//   prim entry [15]=1 [3:0] len0+len1 [6:4] i0 [10:8] i1 : two symbols out of the shortlist
-// shortlist[0..1] = the 8 symbols with the shortest codes (byte j = symbol j), shortlist[2] = their
-// lengths (nibble j).  Codes longer than 8 bits occupy the low end of the index space (canonical
-// order), so the tail needs only x_long entries.
-// ------------------------------------------------------------------------------------------
-constexpr int kPairIndexBits = 11;      // the reference encoder never exceeds 11 (HUF_TABLELOG_DEFAULT)
-constexpr int kPairTailEntries = 256;
-
-// Build the pair table of one chunk (one lane).  t1 = 256 x u16 scratch.  Returns x_long or -1.
-ZB_HD inline int huf_fill_pair_table(uint16_t* prim, uint16_t* tail, uint16_t* t1, uint32_t* shortlist,
-                                               const uint8_t* weights, int nsym, int lg) {
-  if (lg > kPairIndexBits) return -1;
-  uint32_t cnt[kHufLogMax + 2];
-#pragma unroll
-  for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
-  for (int n = 0; n < nsym; n++) cnt[weights[n]]++;
-  const int up = kPairIndexBits - lg;
-  uint32_t start[kHufLogMax + 2];
-  uint32_t at = 0, x_long = 0;
-  start[0] = 0;
-  for (int w = 1; w <= lg; w++) {
-    start[w] = at;
-    const uint32_t span_all = (cnt[w] << (w - 1)) << up;
-    if (lg + 1 - w > 8) x_long = at + span_all;
-    at += span_all;
-  }
-  if (x_long > (uint32_t)kPairTailEntries) return -1;
-  // single-symbol view: t1[k] = symbol << 4 | length, 0 where the code is longer than 8 bits
-  for (uint32_t k = 0; k < (x_long + 7) >> 3; k++) t1[k] = 0;
-  for (int n = 0; n < nsym; n++) {
-    const int w = weights[n];
-    if (w == 0) continue;
-    const int len = lg + 1 - w;
-    const uint32_t span = 1u << (kPairIndexBits - len);
-    const uint32_t u = start[w];
-    start[w] = u + span;
-    if (len > 8) {
-      const uint16_t e = (uint16_t)(n | (len << 8));
-      for (uint32_t q = 0; q < span; q++) tail[u + q] = e;
-    } else {
-      const uint16_t e = (uint16_t)((n << 4) | len);
-      const uint32_t p0 = u >> 3, pn = span >> 3;
-      for (uint32_t q = 0; q < pn; q++) t1[p0 + q] = e;
-    }
-  }
-  // shortlist: the 8 symbols with the shortest codes (<= 7 bits), ties in symbol order
-  uint32_t sl[2] = {0, 0}, sl_len = 0;
-  int have = 0;
-  for (int len = 1; len <= 7 && have < 8; len++) {
-    const int w = lg + 1 - len;
-    if (w < 1 || cnt[w] == 0) continue;
-    for (int n = 0; n < nsym && have < 8; n++)
-      if (weights[n] == w) {
-        sl[have >> 2] |= (uint32_t)n << (8 * (have & 3));
-        sl_len |= (uint32_t)len << (4 * have);
-        have++;
-      }
-  }
-  shortlist[0] = sl[0];
-  shortlist[1] = sl[1];
-  shortlist[2] = sl_len;
-  // pair view
-  for (uint32_t k = 0; k < 256; k++) {
-    const uint32_t e0 = t1[k];
-    uint32_t out = e0;
-    const uint32_t l0 = e0 & 15u;
-    if (l0 != 0 && l0 <= 7) {
-      const uint32_t s0 = e0 >> 4;
-      int i0 = -1;
-      for (int j = 0; j < have; j++)
-        if (((sl[j >> 2] >> (8 * (j & 3))) & 0xFFu) == s0) i0 = j;
-      if (i0 >= 0) {
-        const uint32_t e1 = t1[(k << l0) & 0xFFu];
-        const uint32_t l1 = e1 & 15u;
-        if (l1 != 0 && l0 + l1 <= 8) {
-          const uint32_t s1 = e1 >> 4;
-          int i1 = -1;
-          for (int j = 0; j < have; j++)
-            if (((sl[j >> 2] >> (8 * (j & 3))) & 0xFFu) == s1) i1 = j;
-          if (i1 >= 0) out = 0x8000u | (l0 + l1) | ((uint32_t)i0 << 4) | ((uint32_t)i1 << 8);
-        }
-      }
-    }
-    prim[k] = (uint16_t)out;
-  }
-  return (int)x_long;
-}
-
-
 }  // namespace zb

@@ -44,9 +44,9 @@ inline bool cuda_ok(cudaError_t e) {
 // Off by default.  bench.py turns it on to attribute the step time to kernels; the events
 // sit between launches on the same stream, so they do not change the schedule.
 enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKHufDecodePlanar, kKRegroup, kKEncodeStats, kKEncodeTable, kKEncodeScan, kKEncodeWrite, kKEncodeWriteRagged, kKSplit,
-                kKRegroupPlanar, kKHufDecodePair, kKCount };
+                kKRegroupPlanar, kKCount };
 const char* const kKernelNames[kKCount] = {"k_decode_meta", "k_huf_decode_fused", "k_huf_decode_planar", "k_regroup", "k_encode_hist", "k_encode_table",
-                                           "k_encode_scan", "k_encode_write_warp", "k_encode_write_ragged", "k_split_planar", "k_regroup_planar", "k_huf_decode_pair"};
+                                           "k_encode_scan", "k_encode_write_warp", "k_encode_write_ragged", "k_split_planar", "k_regroup_planar"};
 struct TimedSpan {
   int id;
   cudaEvent_t a, b;
@@ -272,19 +272,9 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   {
     const uint64_t warps = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
-    // The pair-table decoder pays off where the coded plane has short codes: the exponent plane
-    // of the rotated float types (bf16, fp32).  ZIPNN_B200_PAIR=0/1 overrides for experiments.
-    static const int pair_override = [] {
-      const char* e = getenv("ZIPNN_B200_PAIR");
-      return e ? atoi(e) : -1;
-    }();
-    const bool pair = pair_override >= 0 ? pair_override != 0 : (G >= 2 && bits_mode == 1);
-    ScopedTimer tm(pair ? kKHufDecodePair : kKHufDecode, st);
+    ScopedTimer tm(kKHufDecode, st);
     int rc = dispatch_G(G, [&](auto g) -> int {
-      if (pair)
-        k_huf_decode_pair<decltype(g)::value><<<(unsigned)warps, 32, sizeof(PairSmem), st>>>(cfg, (uint8_t*)d_out);
-      else
-        k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, sizeof(FusedSmem), st>>>(cfg, (uint8_t*)d_out);
+      k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, sizeof(FusedSmem), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });
