@@ -38,6 +38,7 @@ struct DecodeCfg {
   uint8_t* planes;      // [slots][G][pstride]
   uint64_t pstride;
   uint32_t max_slots;
+  uint32_t tail_cap;    // entries in the per-warp tail pool of k_huf_decode_fused (multiple of 8)
 };
 
 // ====================================================================================
@@ -156,7 +157,7 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
 constexpr int kDecItemsPerWarp = 8;
 constexpr int kDecLutLog = 11;  // the reference encoder never exceeds 11 (HUF_TABLELOG_DEFAULT)
 constexpr int kDecLutEntries = 1 << kDecLutLog;
-constexpr uint32_t kRingBytes = 128;
+constexpr uint32_t kRingBytes = 64;
 
 struct DecodeSmem {
   uint16_t lut[kDecItemsPerWarp][kDecLutEntries];  // also scratch for the table parse
@@ -204,7 +205,7 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
 #pragma unroll 2
   for (int i = 0; i < maxn; i++) {
     const uint32_t f = b.fetch - 16;
-    // block [f, f+16) replaces ring bytes [f+128, f+144): free once they lie at or above q
+    // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above q
     // (the container and `next` are in registers; later reads are at q - 8 and below)
     if (b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.q) {
       cp_async16(const_cast<uint8_t*>(b.ring) + (f & (kRingBytes - 1)), b.gbase + f);
@@ -262,14 +263,14 @@ struct LutFull {
 // sit at the bottom of the canonical order (index < x_long) and resolve in a tail table
 // indexed by all 11 bits (read only by the lanes that need it).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
-constexpr int kTailEntries = 256;
 struct LutTwo {
-  const uint16_t* tab;   // [0,256): primary, [256, 512): tail
+  const uint16_t* prim;  // 256 entries
+  const uint16_t* tail;  // x_long entries
   uint32_t x_long;
   __device__ __forceinline__ uint32_t get(uint32_t top32) const {
     const uint32_t idx = top32 >> 21;
-    uint32_t e = tab[top32 >> 24];
-    if (idx < x_long) e = tab[256 + idx];
+    uint32_t e = prim[top32 >> 24];
+    if (idx < x_long) e = tail[idx];
     return e;
   }
 };
@@ -286,17 +287,22 @@ __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) 
 // issued first so the copies overlap the decode.
 template <class LUT>
 __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t (&o)[4]) {
-  ring_top_up(b, 2);
-  cp_async_commit();
+  // The ring is 64 bytes: one block is requested per 8 symbols (<= 11 bytes consumed), and a block
+  // is first read at least one half-iteration after the wait that covers it (see ring_top_up).
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    window_refill(b);
-    const uint32_t e0 = window_decode(b, lut), e1 = window_decode(b, lut);
-    window_refill(b);
-    const uint32_t e2 = window_decode(b, lut), e3 = window_decode(b, lut);
-    o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+  for (int h = 0; h < 2; h++) {
+    ring_top_up(b, 1);
+    cp_async_commit();
+#pragma unroll
+    for (int q = 2 * h; q < 2 * h + 2; q++) {
+      window_refill(b);
+      const uint32_t e0 = window_decode(b, lut), e1 = window_decode(b, lut);
+      window_refill(b);
+      const uint32_t e2 = window_decode(b, lut), e3 = window_decode(b, lut);
+      o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+    }
+    cp_async_wait<1>();  // everything but the group just committed has landed
   }
-  cp_async_wait<1>();  // everything but the group just committed has landed
 }
 
 template <class LUT>
@@ -340,27 +346,36 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
   }
 }
 
-// Two-level fill.  Returns the tail size (index bound of the long codes), or -1 when the
-// tail does not fit kTailEntries / the table log exceeds 11 (the caller demotes the chunk).
-__device__ __forceinline__ int fill_lut2(uint16_t* tab, const uint8_t* weights, int nsym, int lg) {
-  uint16_t* prim = tab;
-  uint16_t* tail = tab + 256;
+// Two-level table, step 1: the tail size (index bound of the codes longer than 8 bits) in the
+// 11-bit index space, or -1 when the table log exceeds 11 (the caller demotes the chunk).
+__device__ __forceinline__ int lut2_tail_size(const uint8_t* weights, int nsym, int lg) {
   if (lg > kDecLutLog) return -1;
+  uint32_t cnt[kHufLogMax + 2];
+#pragma unroll
+  for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
+  for (int n = 0; n < nsym; n++) cnt[weights[n]]++;
+  uint32_t at = 0, x_long = 0;
+  for (int w = 1; w <= lg; w++) {
+    at += (cnt[w] << (w - 1)) << (kDecLutLog - lg);
+    if (lg + 1 - w > 8) x_long = at;
+  }
+  return (int)x_long;
+}
+
+// Step 2: fill the 256-entry primary and the x_long-entry tail.
+__device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const uint8_t* weights, int nsym, int lg) {
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
   for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
   for (int n = 0; n < nsym; n++) cnt[weights[n]]++;
   const int up = kDecLutLog - lg;  // replicate into the 11-bit index space
   uint32_t start[kHufLogMax + 2];
-  uint32_t at = 0, x_long = 0;
+  uint32_t at = 0;
   start[0] = 0;
   for (int w = 1; w <= lg; w++) {
     start[w] = at;
-    const uint32_t span_all = (cnt[w] << (w - 1)) << up;
-    if (lg + 1 - w > 8) x_long = at + span_all;
-    at += span_all;
+    at += (cnt[w] << (w - 1)) << up;
   }
-  if (x_long > (uint32_t)kTailEntries) return -1;
   for (int n = 0; n < nsym; n++) {
     const int w = weights[n];
     if (w == 0) continue;
@@ -376,7 +391,6 @@ __device__ __forceinline__ int fill_lut2(uint16_t* tab, const uint8_t* weights, 
       for (uint32_t q = 0; q < pn; q++) prim[p0 + q] = e;
     }
   }
-  return (int)x_long;
 }
 
 struct StreamSetup {
@@ -496,12 +510,32 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 // of elements.  The other planes are loaded as aligned 16-byte blocks one iteration ahead.
 // Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
 // ====================================================================================
+// Shared memory of one warp (dynamic, tail_cap is a launch parameter):
+//   prim  [8][256] u16   4 KiB   primary tables
+//   tail  [tail_cap] u16         tail tables of the 8 chunks packed back to back (bf16 / fp32
+//                                exponent planes need ~16 entries each, fp16 ~90, fp8 ~150)
+//   ring  [32][64]       2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
+//   stage [32][128]      4 KiB   one 128-byte output row per lane, 16-byte units XOR-swizzled;
+//                                the tANS scratch of the parse aliases it (512 B per chunk)
+// 11 KiB with tail_cap = 512 -> 18 warps per SM; 14 KiB with tail_cap = 2048 -> 15.
 struct FusedSmem {
-  uint16_t tab[kDecItemsPerWarp][512];             // primary + tail; also scratch for the table parse
-  __align__(16) uint8_t ring[32][kRingBytes];      // weights[8][256] alias it during the parse
-  __align__(16) uint8_t stage[32][128];            // one 128-byte output row per lane, 16-byte units XOR-swizzled
+  uint16_t (*prim)[256];
+  uint16_t* tail;
+  uint8_t (*ring)[kRingBytes];
+  uint8_t (*stage)[128];
 };
-static_assert(sizeof(FseDecSmall) <= 1024, "small tANS scratch must fit in one table slot");
+__host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap) {
+  return (size_t)kDecItemsPerWarp * 512 + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128;
+}
+__device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw, uint32_t tail_cap) {
+  FusedSmem S;
+  S.prim = reinterpret_cast<uint16_t (*)[256]>(raw);
+  S.tail = reinterpret_cast<uint16_t*>(raw + kDecItemsPerWarp * 512);
+  S.ring = reinterpret_cast<uint8_t (*)[kRingBytes]>(raw + kDecItemsPerWarp * 512 + (size_t)tail_cap * 2);
+  S.stage = reinterpret_cast<uint8_t (*)[128]>(raw + kDecItemsPerWarp * 512 + (size_t)tail_cap * 2 + 32 * kRingBytes);
+  return S;
+}
+static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in 4 stage rows");
 
 struct SidePlane {
   const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
@@ -607,7 +641,7 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut,
 template <int G>
 __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedSmem& S = *reinterpret_cast<FusedSmem*>(smem_raw);
+  const FusedSmem S = fused_smem_carve(smem_raw, cfg.tail_cap);
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t K = cfg.K;
   const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
@@ -622,17 +656,35 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
 
   // ---- table description -> two-level table (lane 0 of each chunk) ----
   int lg = 0, hsize = -1, x_long = 0;
+  uint32_t tail_at = 0;
   {
     uint8_t* weights = &S.ring[0][0] + slot * 256;
-    if (active && stream == 0) {
-      int nsym = 0;
-      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.tab[slot][0]);
+    const bool builder = active && stream == 0;
+    int nsym = 0;
+    if (builder) {
+      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.stage[4 * slot][0]);
       hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
       if (hsize >= 0) {
-        x_long = fill_lut2(S.tab[slot], weights, nsym, lg);
+        x_long = lut2_tail_size(weights, nsym, lg);
         if (x_long < 0) hsize = -1;
       }
-      if (hsize < 0) {
+    }
+    // the 8 tails share one pool: exclusive prefix over the chunks of the warp
+    {
+      const uint32_t mine = (builder && hsize >= 0) ? (uint32_t)x_long : 0u;
+      uint32_t run = mine;
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run += v;
+      }
+      tail_at = run - mine;
+      if (builder && hsize >= 0 && run > cfg.tail_cap) hsize = -1;  // does not fit: general path
+    }
+    if (builder) {
+      if (hsize >= 0) {
+        fill_lut2(S.prim[slot], S.tail + tail_at, weights, nsym, lg);
+      } else {
         // Not an error yet: a table that needs the big scratch, a long tail or log 12, or a
         // corrupt one.  Hand the chunk to the general kernels, which decide.
         const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
@@ -649,7 +701,8 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     lg = __shfl_sync(0xffffffffu, lg, lane & ~3);
     hsize = __shfl_sync(0xffffffffu, hsize, lane & ~3);
     x_long = __shfl_sync(0xffffffffu, x_long, lane & ~3);
-    __syncwarp();  // the ring (aliased by weights) is free from here on
+    tail_at = __shfl_sync(0xffffffffu, tail_at, lane & ~3);
+    __syncwarp();  // the ring and the stage (aliased by the parse scratch) are free from here on
   }
   // From here on no lane leaves early: the output flush is a warp-wide exchange.
   bool live = active && hsize >= 0;
@@ -706,7 +759,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   }
 
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  const LutTwo lut{S.tab[slot], (uint32_t)x_long};
+  const LutTwo lut{S.prim[slot], S.tail + tail_at, (uint32_t)x_long};
   BitWindow b;
   if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
     atomicOr(&cfg.ctrl->error, kErrCorrupt);

@@ -258,6 +258,7 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   cfg.fill = ws + L.fill_off;
   cfg.planes = ws + L.planes_off;
   cfg.pstride = L.pstride;
+  cfg.tail_cap = 0;
   cfg.max_slots = (uint32_t)std::min<uint64_t>((ws_bytes - L.fixed) / ((size_t)G * L.pstride), K);
   const uint64_t nitems = (uint64_t)G * K;
 
@@ -272,9 +273,12 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   {
     const uint64_t warps = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
+    // Tail pool per warp (8 chunks): the exponent planes of the rotated types need ~16 entries
+    // per chunk, fp16 / fp8 planes 90-150; a chunk that does not fit takes the general path.
+    cfg.tail_cap = (G >= 2 && bits_mode == 1) ? 512u : 2048u;
     ScopedTimer tm(kKHufDecode, st);
     int rc = dispatch_G(G, [&](auto g) -> int {
-      k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, sizeof(FusedSmem), st>>>(cfg, (uint8_t*)d_out);
+      k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });
