@@ -189,6 +189,8 @@ struct BitWindow {
   uint32_t c;            // bits consumed from the top of `cont`
   uint32_t q;            // byte offset (from gbase) of the container's lowest byte; moves down by 4
   uint32_t next;         // the word at q - 4
+  uint32_t rd;           // shared-space address of the word at q - 8 (read by the next refill)
+  uint32_t ring_s;       // shared-space address of the ring (64-byte aligned)
   uint32_t fetch;        // byte offset (from gbase) of the lowest 16-byte block already requested
   uint32_t start_bit;    // bit offset (from gbase) of the first stream bit (exact-consumption check)
   const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
@@ -214,12 +216,18 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
   }
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void window_refill(BitWindow& b) {
   if (b.c >= 32u) {
     b.cont = (b.cont << 32) | b.next;
     b.c -= 32u;
     b.q -= 4u;
-    b.next = ring_word(b.ring, b.q - 4u);
+    b.next = lds_u32(b.rd);
+    b.rd = b.ring_s | ((b.rd - 4u) & (kRingBytes - 4u));
   }
 }
 
@@ -244,6 +252,8 @@ __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint
   cp_async_wait<0>();
   b.cont = ((uint64_t)ring_word(ring, b.q + 4u) << 32) | ring_word(ring, b.q);
   b.next = ring_word(ring, b.q - 4u);
+  b.ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  b.rd = b.ring_s | ((b.q - 8u) & (kRingBytes - 4u));
   return true;
 }
 
@@ -263,14 +273,22 @@ struct LutFull {
 // sit at the bottom of the canonical order (index < x_long) and resolve in a tail table
 // indexed by all 11 bits (read only by the lanes that need it).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+  uint32_t v;  // zero-extended; plain asm (not volatile) so the compiler may schedule and predicate it
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 struct LutTwo {
-  const uint16_t* prim;  // 256 entries
-  const uint16_t* tail;  // x_long entries
+  uint32_t prim_s;  // shared-space byte address of the 256-entry primary
+  uint32_t tail_s;  // ... of the x_long-entry tail (32-bit shared addresses: a generic pointer makes
+                    // the compiler rebuild the shared window base for every lookup)
   uint32_t x_long;
   __device__ __forceinline__ uint32_t get(uint32_t top32) const {
     const uint32_t idx = top32 >> 21;
-    uint32_t e = prim[top32 >> 24];
-    if (idx < x_long) e = tail[idx];
+    uint32_t k;  // opaque shift: otherwise the address becomes shift + mask + add instead of shift + IADD3
+    asm("shr.u32 %0, %1, 24;" : "=r"(k) : "r"(top32));
+    uint32_t e = lds_u16(prim_s + k + k);
+    if (idx < x_long) e = lds_u16(tail_s + idx + idx);
     return e;
   }
 };
@@ -458,7 +476,7 @@ __device__ __forceinline__ bool setup_item(DecodeSmem& S, const uint8_t* body, c
 // Kernel 2a: general mode -- decode coded planes into workspace planes.
 // ====================================================================================
 __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t nitems = (uint64_t)cfg.G * cfg.K;
@@ -640,7 +658,7 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut,
 
 template <int G>
 __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const FusedSmem S = fused_smem_carve(smem_raw, cfg.tail_cap);
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t K = cfg.K;
@@ -759,7 +777,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   }
 
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  const LutTwo lut{S.prim[slot], S.tail + tail_at, (uint32_t)x_long};
+  const LutTwo lut{(uint32_t)__cvta_generic_to_shared(S.prim[slot]), (uint32_t)__cvta_generic_to_shared(S.tail + tail_at), (uint32_t)x_long};
   BitWindow b;
   if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
     atomicOr(&cfg.ctrl->error, kErrCorrupt);
