@@ -293,6 +293,76 @@ struct LutTwo {
   }
 };
 
+// Private-column table for planes with short codes (the exponent plane of bf16 / fp32: 98 % of the
+// symbols have codes of <= 6 bits).  The shared 256-entry primary above is read at random words by
+// 32 lanes: ~3.5 bank conflicts per lookup, and the LSU pipe becomes the limit of the whole kernel.
+// Here every lane owns one 4-byte bank column: entry k of lane L is word [k][L] of a [2^PB][32] u32
+// array, indexed by the top PB window bits -- conflict-free by construction.  Codes longer than PB
+// bits resolve in the shared tail (index < x_long), which few lanes touch.
+template <int PB>
+struct LutCol {
+  uint32_t col_s;   // shared-space address of this lane's column (entry 0)
+  uint32_t tail_s;
+  uint32_t x_long;
+  __device__ __forceinline__ uint32_t get(uint32_t top32) const {
+    const uint32_t idx = top32 >> 21;
+    uint32_t k;
+    asm("shr.u32 %0, %1, %2;" : "=r"(k) : "r"(top32), "n"(32 - PB));
+    uint32_t e = lds_u32(col_s + (k << 7));
+    if (idx < x_long) e = lds_u16(tail_s + idx + idx);
+    return e;
+  }
+};
+
+// Tail size for a PB-bit primary: index bound of the codes longer than PB bits (or -1).
+__device__ __forceinline__ int lut_tail_size(const uint8_t* weights, int nsym, int lg, int pb) {
+  if (lg > kDecLutLog) return -1;
+  uint32_t cnt[kHufLogMax + 2];
+#pragma unroll
+  for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
+  for (int n = 0; n < nsym; n++) cnt[weights[n]]++;
+  uint32_t at = 0, x_long = 0;
+  for (int w = 1; w <= lg; w++) {
+    at += (cnt[w] << (w - 1)) << (kDecLutLog - lg);
+    if (lg + 1 - w > pb) x_long = at;
+  }
+  return (int)x_long;
+}
+
+// Fill one lane's column (all 4 lanes of a chunk run it) and, when `with_tail`, the chunk's tail.
+template <int PB>
+__device__ __forceinline__ void fill_lut_col(uint32_t* col /* entry k at col[32 * k] */, uint16_t* tail, bool with_tail,
+                                             const uint8_t* weights, int nsym, int lg) {
+  uint32_t cnt[kHufLogMax + 2];
+#pragma unroll
+  for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
+  for (int n = 0; n < nsym; n++) cnt[weights[n]]++;
+  const int up = kDecLutLog - lg;
+  uint32_t start[kHufLogMax + 2];
+  uint32_t at = 0;
+  start[0] = 0;
+  for (int w = 1; w <= lg; w++) {
+    start[w] = at;
+    at += (cnt[w] << (w - 1)) << up;
+  }
+  for (int n = 0; n < nsym; n++) {
+    const int w = weights[n];
+    if (w == 0) continue;
+    const int len = lg + 1 - w;
+    const uint32_t span = 1u << (kDecLutLog - len);
+    const uint32_t e = (uint32_t)n | ((uint32_t)len << 8);
+    const uint32_t u = start[w];
+    start[w] = u + span;
+    if (len > PB) {
+      if (with_tail)
+        for (uint32_t q = 0; q < span; q++) tail[u + q] = (uint16_t)e;
+    } else {
+      const uint32_t p0 = u >> (kDecLutLog - PB), pn = span >> (kDecLutLog - PB);
+      for (uint32_t q = 0; q < pn; q++) col[32 * (p0 + q)] = e;
+    }
+  }
+}
+
 template <class LUT>
 __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) {
   const uint32_t top32 = (uint32_t)((b.cont << b.c) >> 32);
@@ -535,22 +605,28 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 //   ring  [32][64]       2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
 //   stage [32][128]      4 KiB   one 128-byte output row per lane, 16-byte units XOR-swizzled;
 //                                the tANS scratch of the parse aliases it (512 B per chunk)
-// 11 KiB with tail_cap = 512 -> 18 warps per SM; 14 KiB with tail_cap = 2048 -> 15.
+// Shared primaries: 11 KiB with tail_cap = 512 -> 18 warps per SM; 14 KiB with tail_cap = 2048 -> 15.
+// Private 6-bit columns (8 KiB) + tail_cap 512: 15 KiB -> 14 warps per SM.
 struct FusedSmem {
   uint16_t (*prim)[256];
   uint16_t* tail;
   uint8_t (*ring)[kRingBytes];
   uint8_t (*stage)[128];
 };
-__host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap) {
-  return (size_t)kDecItemsPerWarp * 512 + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128;
+// PB = 0: shared 256-entry u16 primaries (4 KiB); PB > 0: private u32 columns, 2^PB x 32 x 4 bytes.
+__host__ __device__ constexpr size_t fused_prim_bytes(int pb) {
+  return pb == 0 ? (size_t)kDecItemsPerWarp * 512 : ((size_t)128 << pb);
 }
-__device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw, uint32_t tail_cap) {
+__host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap, int pb) {
+  return fused_prim_bytes(pb) + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128;
+}
+__device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw, uint32_t tail_cap, int pb) {
   FusedSmem S;
+  const size_t pbytes = fused_prim_bytes(pb);
   S.prim = reinterpret_cast<uint16_t (*)[256]>(raw);
-  S.tail = reinterpret_cast<uint16_t*>(raw + kDecItemsPerWarp * 512);
-  S.ring = reinterpret_cast<uint8_t (*)[kRingBytes]>(raw + kDecItemsPerWarp * 512 + (size_t)tail_cap * 2);
-  S.stage = reinterpret_cast<uint8_t (*)[128]>(raw + kDecItemsPerWarp * 512 + (size_t)tail_cap * 2 + 32 * kRingBytes);
+  S.tail = reinterpret_cast<uint16_t*>(raw + pbytes);
+  S.ring = reinterpret_cast<uint8_t (*)[kRingBytes]>(raw + pbytes + (size_t)tail_cap * 2);
+  S.stage = reinterpret_cast<uint8_t (*)[128]>(raw + pbytes + (size_t)tail_cap * 2 + 32 * kRingBytes);
   return S;
 }
 static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in 4 stage rows");
@@ -559,12 +635,12 @@ struct SidePlane {
   const uint4* blk;  // aligned block holding the plane byte that pairs with the lane's next symbol
   uint32_t shift;    // byte offset (0..15) of that byte inside the block
   uint32_t step;     // 1 for stream bytes, 0 for an RLE fill block
-  uint4 a, b;        // blocks k, k+1 (k+2 is in flight in `c`)
-  uint4 c;
+  uint4 a, b;        // blocks k, k+1
+  uint4 c, d;        // blocks k+2, k+3 in flight: two iterations of distance, because ptxas sinks a
+                     // load towards its first use and a distance of one iteration ends up as none
 };
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
-
 // 16 bytes starting `shift` bytes into the 32-byte pair (a, b).
 __device__ __forceinline__ void take16(const uint4& a, const uint4& b, uint32_t shift, uint32_t (&out)[4]) {
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -590,7 +666,7 @@ __device__ __forceinline__ void unrotate_planes(uint32_t& lo, uint32_t& hi) {
 }
 
 // One iteration: 16 symbols of the coded (top) plane + the matching bytes of the G-1 other
-// planes -> 16*G bytes of elements.  kGuard = clamp the look-ahead block loads to the end of
+// planes -> 16*G bytes of elements.  guard = clamp the look-ahead block loads to the end of
 // the stream buffer (only the last iterations of a stream can reach past it).
 // Output rows.  A lane produces 16*G bytes per iteration, 64 KiB away from its neighbours'
 // data, so direct stores cost one LSU wavefront per lane.  Instead each lane fills a 128-byte
@@ -603,17 +679,17 @@ __device__ __forceinline__ uint4* stage_unit(uint8_t (*stage)[128], int row, int
 
 // One iteration: 16 symbols of the coded (top) plane + the matching bytes of the G-1 other
 // planes -> 16*G bytes of elements into units [unit0, unit0+G) of the lane's stage row.
-// kGuard = clamp the look-ahead block loads to the end of the stream buffer (only the last
+// guard = clamp the look-ahead block loads to the end of the stream buffer (only the last
 // iterations of a stream can reach past it).
-template <int G, bool kGuard>
-__device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
-                                                const uint4* hi_block, bool rot, uint8_t (*stage)[128], int lane, int unit0) {
+template <int G, class LUT>
+__device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
+                                                const uint4* hi_block, bool guard, bool rot, uint8_t (*stage)[128], int lane, int unit0) {
   if (G > 1) {
 #pragma unroll
-    for (int g = 0; g < G - 1; g++) {  // block k+2 of every side plane, used next iteration
-      const uint4* nb = side[g].blk + 2 * side[g].step;
-      if (kGuard && nb > hi_block) nb = hi_block;
-      side[g].c = ldg128(nb);
+    for (int g = 0; g < G - 1; g++) {  // block k+3 of every side plane, used two iterations later
+      const uint4* nb = side[g].blk + 3 * side[g].step;
+      if (guard && side[g].step && nb > hi_block) nb = hi_block;  // (an RLE fill block lives in the workspace)
+      side[g].d = ldg128(nb);
     }
   }
   uint32_t pl[G][4];
@@ -652,14 +728,16 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LutTwo& lut,
   for (int g = 0; g < G - 1; g++) {
     side[g].a = side[g].b;
     side[g].b = side[g].c;
+    side[g].c = side[g].d;
     side[g].blk += side[g].step;
   }
 }
 
-template <int G>
+template <int G, int PB>
 __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const FusedSmem S = fused_smem_carve(smem_raw, cfg.tail_cap);
+  const FusedSmem S = fused_smem_carve(smem_raw, cfg.tail_cap, PB);
+  using LUT = typename std::conditional<PB == 0, LutTwo, LutCol<(PB ? PB : 1)>>::type;
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t K = cfg.K;
   const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
@@ -683,7 +761,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.stage[4 * slot][0]);
       hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
       if (hsize >= 0) {
-        x_long = lut2_tail_size(weights, nsym, lg);
+        x_long = PB == 0 ? lut2_tail_size(weights, nsym, lg) : lut_tail_size(weights, nsym, lg, PB);
         if (x_long < 0) hsize = -1;
       }
     }
@@ -701,7 +779,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     }
     if (builder) {
       if (hsize >= 0) {
-        fill_lut2(S.prim[slot], S.tail + tail_at, weights, nsym, lg);
+        if (PB == 0) fill_lut2(S.prim[slot], S.tail + tail_at, weights, nsym, lg);
       } else {
         // Not an error yet: a table that needs the big scratch, a long tail or log 12, or a
         // corrupt one.  Hand the chunk to the general kernels, which decide.
@@ -720,6 +798,11 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     hsize = __shfl_sync(0xffffffffu, hsize, lane & ~3);
     x_long = __shfl_sync(0xffffffffu, x_long, lane & ~3);
     tail_at = __shfl_sync(0xffffffffu, tail_at, lane & ~3);
+    if (PB != 0) {  // private columns: the 4 lanes of a chunk fill their own copy in parallel
+      nsym = __shfl_sync(0xffffffffu, nsym, lane & ~3);
+      if (active && hsize >= 0)
+        fill_lut_col<(PB ? PB : 1)>(reinterpret_cast<uint32_t*>(smem_raw) + lane, S.tail + tail_at, stream == 0, weights, nsym, lg);
+    }
     __syncwarp();  // the ring and the stage (aliased by the parse scratch) are free from here on
   }
   // From here on no lane leaves early: the output flush is a warp-wide exchange.
@@ -773,11 +856,20 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       side[g].a = ldg128(side[g].blk);
       const uint4* nb = side[g].blk + side[g].step;
       side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+      nb += side[g].step;
+      side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
     }
   }
 
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  const LutTwo lut{(uint32_t)__cvta_generic_to_shared(S.prim[slot]), (uint32_t)__cvta_generic_to_shared(S.tail + tail_at), (uint32_t)x_long};
+  LUT lut;
+  if constexpr (PB == 0) {
+    lut.prim_s = (uint32_t)__cvta_generic_to_shared(S.prim[slot]);
+  } else {
+    lut.col_s = (uint32_t)__cvta_generic_to_shared(smem_raw) + 4u * (uint32_t)lane;
+  }
+  lut.tail_s = (uint32_t)__cvta_generic_to_shared(S.tail + tail_at);
+  lut.x_long = (uint32_t)x_long;
   BitWindow b;
   if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
     atomicOr(&cfg.ctrl->error, kErrCorrupt);
@@ -803,13 +895,12 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
 
   for (uint32_t row = 0; row < max_rows; row++) {
     if (row < my_rows) {
-      if (row + 1 < my_rows) {
-#pragma unroll
-        for (int k = 0; k < kIters; k++) fused_iteration<G, false>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
-      } else {  // the look-ahead loads of the last row may reach past the plane
-#pragma unroll
-        for (int k = 0; k < kIters; k++) fused_iteration<G, true>(b, lut, side, hi_block, rot, S.stage, lane, k * G);
-      }
+      // NOT unrolled: inside straight-line code ptxas sinks the side-plane loads next to their first
+      // use (measured: 25 % of all stall samples on that use); across a loop back-edge it cannot,
+      // so a block requested in trip k is at least one whole trip old when trip k+2 consumes it.
+      const bool guard = row + 2 >= my_rows;  // look-ahead of 3 blocks: clamp in the last two rows
+#pragma unroll 1
+      for (int k = 0; k < kIters; k++) fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G);
     }
     __syncwarp();
 #pragma unroll

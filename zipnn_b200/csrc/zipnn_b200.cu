@@ -273,12 +273,19 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   {
     const uint64_t warps = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
-    // Tail pool per warp (8 chunks): the exponent planes of the rotated types need ~16 entries
-    // per chunk, fp16 / fp8 planes 90-150; a chunk that does not fit takes the general path.
-    cfg.tail_cap = (G >= 2 && bits_mode == 1) ? 512u : 2048u;
+    // Short-code planes (the exponent plane of the rotated types, ~2.6 bits per symbol) use
+    // conflict-free private 6-bit table columns and a small tail pool (8 chunks x ~48 entries);
+    // fp16 / fp8 planes (6-7 bits per symbol, 90-150 tail entries per chunk) keep the shared
+    // 8-bit primaries.  A chunk whose tail does not fit the pool takes the general path.
+    const bool short_codes = (G >= 2 && bits_mode == 1);
+    cfg.tail_cap = short_codes ? 512u : 2048u;
     ScopedTimer tm(kKHufDecode, st);
     int rc = dispatch_G(G, [&](auto g) -> int {
-      k_huf_decode_fused<decltype(g)::value><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap), st>>>(cfg, (uint8_t*)d_out);
+      constexpr int GG = decltype(g)::value;
+      if (short_codes)
+        k_huf_decode_fused<GG, 6><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 6), st>>>(cfg, (uint8_t*)d_out);
+      else
+        k_huf_decode_fused<GG, 0><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 0), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });
