@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 //   stage [32][128]      4 KiB   one 128-byte output row per lane, 16-byte units XOR-swizzled;
 //                                the tANS scratch of the parse aliases it (512 B per chunk)
 // Shared primaries: 11 KiB with tail_cap = 512 -> 18 warps per SM; 14 KiB with tail_cap = 2048 -> 15.
-// Private 6-bit columns (8 KiB) + tail_cap 512: 15 KiB -> 14 warps per SM.
+// Private 5-bit columns (4 KiB) + tail_cap 1024: 12 KiB -> 17 warps per SM.
 struct FusedSmem {
   uint16_t (*prim)[256];
   uint16_t* tail;

@@ -274,16 +274,18 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     const uint64_t warps = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
     // Short-code planes (the exponent plane of the rotated types, ~2.6 bits per symbol) use
-    // conflict-free private 6-bit table columns and a small tail pool (8 chunks x ~48 entries);
-    // fp16 / fp8 planes (6-7 bits per symbol, 90-150 tail entries per chunk) keep the shared
-    // 8-bit primaries.  A chunk whose tail does not fit the pool takes the general path.
+    // conflict-free private 5-bit table columns (4 KiB) and a 1024-entry tail pool (8 chunks x
+    // ~64-100 entries for the codes longer than 5 bits): 12 KiB per warp, 17 warps per SM.
+    // Measured on 16 GiB bf16: 4 or 5 bits 10.9 ms, 6 bits 11.3, 7 bits (9 warps) 13.4, shared
+    // 8-bit primaries 11.5.  fp16 / fp8 planes (6-7 bits per symbol, 90-150 entries of > 8 bits per
+    // chunk) keep the shared 8-bit primaries.  A chunk whose tail does not fit takes the general path.
     const bool short_codes = (G >= 2 && bits_mode == 1);
-    cfg.tail_cap = short_codes ? 512u : 2048u;
+    cfg.tail_cap = short_codes ? 1024u : 2048u;
     ScopedTimer tm(kKHufDecode, st);
     int rc = dispatch_G(G, [&](auto g) -> int {
       constexpr int GG = decltype(g)::value;
       if (short_codes)
-        k_huf_decode_fused<GG, 6><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 6), st>>>(cfg, (uint8_t*)d_out);
+        k_huf_decode_fused<GG, 5><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 5), st>>>(cfg, (uint8_t*)d_out);
       else
         k_huf_decode_fused<GG, 0><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 0), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
