@@ -321,3 +321,26 @@ def test_pipelined_host_decompress(monkeypatch):
         bad[hdr_len + 1] = 9        # a type byte out of range is always detectable
         with pytest.raises(RuntimeError, match="corrupt"):
             ZipNN(input_format="torch").decompress(bytes(bad))
+
+
+@pytest.mark.gpu
+def test_pipelined_host_compress(monkeypatch):
+    """Large host inputs are compressed slab by slab (H2D of the next slab, D2H of group 0 of the
+    previous one in flight together); the stream must equal the one-shot device stream byte for byte."""
+    import zipnn_b200.zipnn as zz
+    g = torch.Generator().manual_seed(7)
+    cases = ((torch.bfloat16, 5 * 131072 * 2 + 12345), (torch.float32, 11 * 65536 + 7), (torch.float16, 7 * 131072),
+             (torch.float8_e4m3fn, 9 * 131072 + 1))
+    for dt, n in cases:
+        t = (torch.randn(n, generator=g) * 0.02).to(dt)
+        t[1000:200000] = 0  # RLE planes in some chunks
+        one_shot = ZipNN(input_format="torch").compress(t.cuda()).cpu().numpy().tobytes()
+        with monkeypatch.context() as m:
+            m.setattr(zz, "PIPELINE_MIN_BYTES", 1 << 20)
+            m.setattr(zz, "PIPELINE_SLAB_BYTES", 3 * 262144)
+            piped = bytes(ZipNN(input_format="torch").compress(t))
+            out = torch.empty(len(one_shot) + 4096, dtype=torch.uint8, pin_memory=True)
+            piped_out = bytes(ZipNN(input_format="torch").compress(t.pin_memory(), out=out))
+        assert piped == one_shot and piped_out == one_shot, str(dt)
+        back = ZipNN(input_format="torch").decompress(piped)
+        assert raw_bytes(back) == raw_bytes(t)

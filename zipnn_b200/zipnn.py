@@ -471,6 +471,8 @@ def _compress_host(flat_u8, header: bytes, num_buf: int, bits_mode: int, bytes_m
     """Host bytes in, host bytes out: H2D copy, GPU codec, D2H copy of exactly the stream."""
     _native.require_cuda()
     src = _host_tensor(flat_u8)
+    if src.numel() >= PIPELINE_MIN_BYTES and src.numel() > PIPELINE_SLAB_BYTES:
+        return _compress_host_pipelined(src, header, num_buf, bits_mode, bytes_mode, chunk, threshold, out)
     dev_in = torch.empty(src.numel(), dtype=torch.uint8, device="cuda")
     dev_in.copy_(src, non_blocking=True)
     stream = _compress_device(dev_in, header, num_buf, bits_mode, bytes_mode, chunk, threshold)
@@ -478,6 +480,112 @@ def _compress_host(flat_u8, header: bytes, num_buf: int, bits_mode: int, bytes_m
     host.copy_(stream, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return memoryview(host.numpy())
+
+
+def _compress_host_pipelined(src: torch.Tensor, header: bytes, G: int, bits_mode: int, bytes_mode: int, chunk: int,
+                             threshold: float, out=None):
+    """Large host inputs go through the device slab by slab so that PCIe runs in both directions at
+    once.  Chunks are independent (a slab compressed alone yields the same per-chunk payloads, the
+    construction zipnn_b200.sharded uses across GPUs), and in the stream layout
+    `[header][types][cum][group 0 payloads][group 1 payloads]...` (csrc/zipnn_core.c:105-244) the
+    position of group 0's payload of a slab depends only on the slabs before it.  So while slab i+1
+    is on its way in, slab i is compressed and its group-0 payload (the raw sign/mantissa plane of
+    bf16: 3/4 of the stream) is already on its way out to its final place; the other groups wait on
+    the device until group 0's total is known.  The tables and the header are assembled on the host."""
+    L = _native.lib()
+    n = src.numel()
+    K = (n + chunk - 1) // chunk
+    per = max(1, PIPELINE_SLAB_BYTES // chunk)
+    slabs = [(c0, min(K, c0 + per)) for c0 in range(0, K, per)]
+    hdr_len = len(header)
+    payload0 = hdr_len + 9 * G * K
+    if out is None:
+        host = _host_out(_native.compress_bound(n, G, chunk, hdr_len), None)
+    else:   # the size is not known in advance: use whatever room the caller gave, check as we go
+        host = _host_out(0, out)
+        host = out.detach().reshape(-1)
+        host = host if host.dtype == torch.uint8 else host.view(torch.uint8)
+    cap = host.numel()
+    if cap < payload0:
+        raise ValueError("out= must be a contiguous CPU tensor with room for the result")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    slab_hdr = bytes(32)
+    slab_bytes_max = per * chunk
+    sbound = (_native.compress_bound(slab_bytes_max, G, chunk, 32) + 255) & ~255
+    held = torch.empty(sbound * len(slabs), dtype=torch.uint8, device=dev)       # every slab's stream stays on the device
+    nst = 2
+    streams = [torch.cuda.Stream() for _ in range(nst)]
+    out_stream = torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+    dins = [torch.empty(slab_bytes_max, dtype=torch.uint8, device=dev) for _ in range(nst)]
+    wss = [torch.empty(_native.compress_workspace_size(slab_bytes_max, G, chunk), dtype=torch.uint8, device=dev) for _ in range(nst)]
+    hdr_c = (C.c_char * 32).from_buffer_copy(slab_hdr)
+    types_all = np.empty((G, K), dtype=np.uint8)
+    cum_all = np.empty((G, K), dtype=np.int64)
+    run = np.zeros(G, dtype=np.int64)              # bytes of each group in the slabs before this one
+    slab_off = []                                  # per slab: payload offset inside `held` of each group, sizes
+    for st in streams:
+        st.wait_stream(cur)
+    out_stream.wait_stream(cur)
+
+    def upload(i):
+        c0, c1 = slabs[i]
+        b0, b1 = c0 * chunk, min(n, c1 * chunk)
+        with torch.cuda.stream(streams[i % nst]):
+            dins[i % nst][: b1 - b0].copy_(src[b0:b1], non_blocking=True)
+
+    upload(0)
+    for i, (c0, c1) in enumerate(slabs):
+        k = i % nst
+        Ks = c1 - c0
+        nb = min(n, c1 * chunk) - c0 * chunk
+        if i + 1 < len(slabs):
+            upload(i + 1)                          # in flight while slab i is compressed and copied out
+        dst = held[i * sbound: (i + 1) * sbound]
+        out_len = C.c_size_t(0)
+        _native.check(L.zipnn_b200_compress(dins[k].data_ptr(), nb, hdr_c, 32, G, bits_mode, bytes_mode, chunk, threshold,
+                                            dst.data_ptr(), sbound, C.byref(out_len), wss[k].data_ptr(), wss[k].numel(),
+                                            streams[k].cuda_stream))        # returns when the slab's stream is complete
+        with torch.cuda.stream(streams[k]):
+            meta = dst[32: 32 + 9 * G * Ks].cpu().numpy()
+        types_all[:, c0:c1] = meta[: G * Ks].reshape(G, Ks)
+        cs = meta[G * Ks:].view("<u8").reshape(G, Ks).astype(np.int64)
+        cum_all[:, c0:c1] = cs + run.reshape(G, 1)
+        tot = cs[:, -1]
+        offs = 32 + 9 * G * Ks + np.concatenate([[0], np.cumsum(tot)[:-1]])
+        if 32 + 9 * G * Ks + int(tot.sum()) != out_len.value:
+            raise RuntimeError("zipnn_b200: inconsistent slab stream")
+        slab_off.append((offs, tot, run.copy()))
+        if tot[0]:
+            with torch.cuda.stream(out_stream):
+                a = payload0 + int(run[0])
+                if a + int(tot[0]) > cap:
+                    raise ValueError("out= must be a contiguous CPU tensor with room for the result")
+                host[a: a + int(tot[0])].copy_(dst[int(offs[0]): int(offs[0]) + int(tot[0])], non_blocking=True)
+        run += tot
+    base = payload0 + np.concatenate([[0], np.cumsum(run)[:-1]])
+    total = payload0 + int(run.sum())
+    if total > cap:
+        raise ValueError("out= must be a contiguous CPU tensor with room for the result")
+    with torch.cuda.stream(out_stream):
+        for g in range(1, G):
+            for i in range(len(slabs)):
+                offs, tot, before = slab_off[i]
+                if tot[g]:
+                    a = int(base[g] + before[g])
+                    o = i * sbound + int(offs[g])
+                    host[a: a + int(tot[g])].copy_(held[o: o + int(tot[g])], non_blocking=True)
+    # header (total length at [24:32], csrc/zipnn_core.c:121) and the two tables, written by the host
+    hb = bytearray(header)
+    hb[24:32] = int(total).to_bytes(8, "little")
+    hv = host.numpy()
+    hv[:hdr_len] = np.frombuffer(bytes(hb), dtype=np.uint8)
+    hv[hdr_len: hdr_len + G * K] = types_all.reshape(-1)
+    hv[hdr_len + G * K: payload0] = cum_all.astype("<u8").reshape(-1).view(np.uint8)
+    out_stream.synchronize()
+    for st in streams:
+        cur.wait_stream(st)
+    return memoryview(hv[:total])
 
 
 # Host streams at least this large are decoded slab by slab on two CUDA streams, so the H2D
