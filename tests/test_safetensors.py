@@ -106,3 +106,45 @@ def test_tiny_tensors_survive_the_raw_fallback(tmp_path):
         assert "tiny" not in f.compressed_tensors_metadata and "big" in f.compressed_tensors_metadata
         for name, t in tensors.items():
             assert _same(f.get_tensor(name), t), name
+
+
+@pytest.mark.gpu
+def test_gpu_load_path_many_tensors_and_deferred_errors(tmp_path):
+    """SafeOpen(device="cuda") decodes on side streams without a host sync per tensor: every tensor
+    must still be exact when used on the current stream, and a corrupt entry must raise when the
+    file is closed."""
+    from safetensors.torch import save_file as sf
+    from zipnn_b200 import SafeOpen, compress_safetensors_file, load_file
+    g = torch.Generator().manual_seed(3)
+    want = {}
+    for i in range(40):
+        dt = (torch.bfloat16, torch.float32, torch.float16)[i % 3]
+        n = (1, 17, 4096, 70000, 300001, 1 << 20)[i % 6]
+        want[f"t{i}"] = (torch.randn(n, generator=g) * 0.02).to(dt)
+    want["ids"] = torch.arange(100, dtype=torch.int64)
+    src = tmp_path / "many.safetensors"
+    sf(want, str(src))
+    path, _, _ = compress_safetensors_file(str(src))
+    got = load_file(path, "cuda")
+    assert set(got) == set(want)
+    for k, t in want.items():
+        assert got[k].is_cuda and got[k].dtype == t.dtype and tuple(got[k].shape) == tuple(t.shape)
+        assert torch.equal(got[k].cpu().view(torch.uint8), t.view(torch.uint8)), k
+    # results are usable immediately on the current stream (no explicit sync by the caller)
+    with SafeOpen(path, "pt", "cuda") as f:
+        acc = sum(float(f.get_tensor(k).float().sum()) for k in want if k != "ids")
+    ref = sum(float(t.float().sum()) for k, t in want.items() if k != "ids")
+    assert abs(acc - ref) < 1e-2 * max(1.0, abs(ref))
+    # corrupt one compressed entry's type byte inside the file -> error when the file is closed
+    import json, struct
+    blob = bytearray(open(path, "rb").read())
+    hlen = struct.unpack("<Q", blob[:8])[0]
+    meta = json.loads(bytes(blob[8: 8 + hlen]))
+    a, _ = meta["t5"]["data_offsets"]
+    blob[8 + hlen + a + 32 + 1 + 1 + 4 + 0] = 9        # first type byte after the 38-byte header (1-D shape < 2^32)
+    bad = tmp_path / "bad.znn.safetensors"
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises(RuntimeError, match="corrupt"):
+        with SafeOpen(str(bad), "pt", "cuda") as f:
+            for k in f.keys():
+                f.get_tensor(k)

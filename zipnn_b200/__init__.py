@@ -5,9 +5,9 @@ Drop-in for the reference package surface that sits on the hot path
 transformers monkey-patch, zipnn/zipnn.py:1221-1565) is file plumbing outside the path and
 is not provided.
 """
-from .zipnn import ZipNN
+from .zipnn import DecodePipe, ZipNN
 from .safetensors_io import (SafeOpen, compress_safetensors_file, decompress_safetensors_file,
-                             decompress_safetensors_tensor, zipnn_safetensors)
+                             decompress_safetensors_tensor, load_file, zipnn_safetensors)
 
 
 def zipnn_hf(*args, **kwargs):
@@ -16,4 +16,4 @@ def zipnn_hf(*args, **kwargs):
 
 
 __all__ = ["ZipNN", "zipnn_safetensors", "SafeOpen", "compress_safetensors_file",
-           "decompress_safetensors_file", "decompress_safetensors_tensor", "zipnn_hf"]
+           "decompress_safetensors_file", "decompress_safetensors_tensor", "load_file", "DecodePipe", "zipnn_hf"]

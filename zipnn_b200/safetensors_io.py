@@ -23,7 +23,7 @@ from .util_patch import multi_process_patcher
 from .util_safetensors import (COMPRESSED_DTYPE, COMPRESSION_METHOD, build_compressed_tensor_info,
                                get_compressed_tensors_metadata, set_compressed_tensors_metadata)
 from .util_torch import zipnn_is_floating_point
-from .zipnn import ZipNN
+from .zipnn import DecodePipe, ZipNN
 
 
 def decompress_safetensors_tensor(tensor: torch.Tensor, device=None) -> torch.Tensor:
@@ -36,21 +36,58 @@ def decompress_safetensors_tensor(tensor: torch.Tensor, device=None) -> torch.Te
     return znn.decompress(tensor.contiguous())
 
 
+def _safetensors_index(filename) -> dict:
+    """{tensor name: (absolute file offset, byte length)} from the safetensors header
+    (8-byte little-endian length, JSON with `data_offsets` relative to the end of the header)."""
+    import json
+    with open(filename, "rb") as f:
+        hlen = int.from_bytes(f.read(8), "little")
+        meta = json.loads(f.read(hlen))
+    base = 8 + hlen
+    return {k: (base + v["data_offsets"][0], v["data_offsets"][1] - v["data_offsets"][0])
+            for k, v in meta.items() if k != "__metadata__"}
+
+
 class SafeOpen:
     """`safetensors.safe_open` wrapper that decodes compressed tensors on access
     (zipnn/zipnn.py:1592-1626)."""
 
     def __init__(self, filename, framework, device="cpu"):
         self._device = device
+        self._filename = filename
         self._f = _safe_open(filename, framework, device)
         self.compressed_tensors_metadata = get_compressed_tensors_metadata(self._f.metadata())
+        dev = torch.device(device) if isinstance(device, (str, torch.device)) else torch.device("cuda", device)
+        self._cuda = dev if dev.type == "cuda" else None
+        self._fd = None         # own descriptor: compressed bytes are read straight into pinned staging slabs
+        self._index = None
+        self._pipe = None
 
     def get_tensor(self, name):
         if name not in self.compressed_tensors_metadata:
             return self._f.get_tensor(name)
-        raw = self._f.get_tensor(name)
-        dev = torch.device(self._device) if isinstance(self._device, (str, torch.device)) else torch.device("cuda", self._device)
-        return decompress_safetensors_tensor(raw, device=dev if dev.type == "cuda" else None)
+        if self._cuda is None:
+            return decompress_safetensors_tensor(self._f.get_tensor(name))
+        # GPU load path: header parsed on the host, compressed bytes through a pinned staging buffer,
+        # decode on a side stream, no host synchronisation per tensor (errors surface in close()).
+        if self._pipe is None:
+            self._index = _safetensors_index(self._filename)
+            self._fd = os.open(self._filename, os.O_RDONLY)
+            self._pipe = DecodePipe(self._cuda)
+        off, nbytes = self._index[name]
+        znn = ZipNN(input_format="torch", bytearray_dtype=COMPRESSED_DTYPE, method=COMPRESSION_METHOD)
+        return self._pipe.submit_file(self._fd, off, nbytes, znn)
+
+    def close(self):
+        """Wait for the decodes still in flight and raise what they found (corrupt stream, ...)."""
+        pipe, self._pipe = self._pipe, None
+        fd, self._fd = self._fd, None
+        try:
+            if pipe is not None:
+                pipe.finish()
+        finally:
+            if fd is not None:
+                os.close(fd)
 
     def get_slice(self, name):
         if name not in self.compressed_tensors_metadata:
@@ -61,10 +98,36 @@ class SafeOpen:
         return self
 
     def __exit__(self, exc_type, exc_value, traceback):
-        return self._f.__exit__(exc_type, exc_value, traceback)
+        try:
+            if exc_type is None:
+                self.close()
+        finally:
+            self._pipe = None
+            if self._fd is not None:
+                os.close(self._fd)
+                self._fd = None
+            r = self._f.__exit__(exc_type, exc_value, traceback)
+        return r
+
+    def __del__(self):
+        try:
+            if self._pipe is not None:
+                self._pipe.finish()
+        except Exception:
+            pass
 
     def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
         return getattr(self._f, name)
+
+
+def load_file(filename, device="cpu") -> dict:
+    """Whole-file load (the shape of `safetensors.torch.load_file`): every tensor of a
+    `.znn.safetensors` (or plain) file, compressed entries decoded -- on the GPU, many at a time,
+    when `device` is a CUDA device."""
+    with SafeOpen(filename, "pt", device) as f:
+        return {name: f.get_tensor(name) for name in f.keys()}
 
 
 def _zipnn_safetensors():
