@@ -630,6 +630,15 @@ constexpr int kWbWarps = 4;
 constexpr uint32_t kWbTile = 512;                          // plane bytes per warp step (16 per lane)
 constexpr uint32_t kWbBitWords = (kWbTile * 11) / 32 + 4;  // worst-case tile bits + carry
 
+// (lo, hi) = 4 bytes each of the two top byte planes of 4 elements; the element-level rotation
+// [sign][exp8][mant] -> [exp8][sign][mant] (data_manipulation_dtype16.c:10-20, dtype32.c:39-49) becomes
+// hi' = exp8 = hi << 1 | lo >> 7, lo' = sign | low 7 bits, per byte.
+__device__ __forceinline__ void rotate_planes(uint32_t& lo, uint32_t& hi) {
+  const uint32_t l = lo, h = hi;
+  hi = ((h << 1) & 0xFEFEFEFEu) | ((l >> 7) & 0x01010101u);
+  lo = (h & 0x80808080u) | (l & 0x7F7F7F7Fu);
+}
+
 struct WbItem {
   uint8_t* dest;
   uint32_t size;
@@ -777,11 +786,13 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
         for (int i = 0; i < G; i++) {
           w[4 * i] = cur[i].x; w[4 * i + 1] = cur[i].y; w[4 * i + 2] = cur[i].z; w[4 * i + 3] = cur[i].w;
         }
-        if (rot) {
-#pragma unroll
-          for (int i = 0; i < 4 * G; i++) w[i] = rot_word<G>(w[i]);
-        }
         split16<G>(w, pv);
+        if (rot) {  // sign-bit rotation at plane level: 4 operations per 4 elements instead of 5 per word
+          rotate_planes(pv[(G - 2) % G].x, pv[G - 1].x);
+          rotate_planes(pv[(G - 2) % G].y, pv[G - 1].y);
+          rotate_planes(pv[(G - 2) % G].z, pv[G - 1].z);
+          rotate_planes(pv[(G - 2) % G].w, pv[G - 1].w);
+        }
       }
 #pragma unroll
       for (int g = 0; g < G; g++) {
