@@ -865,19 +865,21 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
           const uint32_t tile_bits = __shfl_sync(0xffffffffu, x, 0);
           uint32_t* bitbuf = S.bitbuf[warp][g];
           uint32_t off = (st[g].B - 32 * st[g].flushed) + (x - mine);
+          // Branch-free: a run of <= 44 bits touches words wi, wi+1 (always written, OR of 0 is harmless,
+          // an idle lane of the last partial tile ORs zeros at a valid offset) and, when it starts past
+          // bit 20, wi+2 (predicated reduction, no branch around it).
+          const uint32_t bitbuf_s = (uint32_t)__cvta_generic_to_shared(bitbuf);
 #pragma unroll
           for (int r = 0; r < 4; r++) {
-            if (l[r]) {
-              const uint32_t sh = off & 31, wi = off >> 5;
-              const uint32_t lo32 = (uint32_t)v[r], hi32 = (uint32_t)(v[r] >> 32);
-              const uint32_t w0 = lo32 << sh;
-              const uint32_t w1 = __funnelshift_l(lo32, hi32, sh);
-              const uint32_t w2 = sh ? (hi32 >> (32 - sh)) : 0u;
-              if (w0) atomicOr(&bitbuf[wi], w0);
-              if (w1) atomicOr(&bitbuf[wi + 1], w1);
-              if (w2) atomicOr(&bitbuf[wi + 2], w2);
-              off += l[r];
-            }
+            const uint32_t sh = off & 31, sa = bitbuf_s + ((off >> 5) << 2);
+            const uint32_t lo32 = (uint32_t)v[r], hi32 = (uint32_t)(v[r] >> 32);
+            const uint32_t w0 = lo32 << sh;
+            const uint32_t w1 = __funnelshift_l(lo32, hi32, sh);
+            const uint32_t w2 = (hi32 >> 1) >> (31 - sh);
+            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(w0) : "memory");
+            asm volatile("red.shared.or.b32 [%0+4], %1;" ::"r"(sa), "r"(w1) : "memory");
+            asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.or.b32 [%0+8], %1; }" ::"r"(sa), "r"(w2) : "memory");
+            off += l[r];
           }
           __syncwarp();
           st[g].B += tile_bits;
