@@ -56,10 +56,13 @@ __device__ __forceinline__ uint32_t rot_byte_at(const uint8_t* __restrict__ in_c
 // byte including the atomic; the first version spent 11).  Per stream quarter the columns are
 // folded into hist[item][stream][256] (u16) in global memory for pass A2.
 // =====================================================================================
+// Columns per bin.  32 = one per lane: no two lanes of a warp ever meet in a bank (1 wavefront per
+// atomic instead of 2), at 32 KiB of counters per plane; fp32 has four planes and keeps 16.
+// Measured on 16 GiB bf16: 16 columns 5.84 ms, 32 columns 5.07 ms, + two quarters per fold 4.61 ms.
 template <int G>
 struct HistCfg {
-  static constexpr int R = (G == 4) ? 8 : 16;          // columns per bin
-  static constexpr int kShift = (G == 4) ? 5 : 6;      // log2(R * 4): byte offset of a bin
+  static constexpr int R = (G == 4) ? 16 : 32;
+  static constexpr int kShift = (G == 4) ? 6 : 7;      // log2(R * 4): byte offset of a bin
 };
 
 template <int G>
@@ -86,6 +89,10 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
     const uint32_t rot_words = (bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;
     const bool fast = (chunk_len % 64u) == 0;
     for (int q = 0; q < 4; q++) {
+      // Two stream quarters share one fold: quarter q counts in the low (q even) or high (q odd) half
+      // of the 32-bit counters.  A column receives at most 8 threads x 128 bytes = 1024 per quarter,
+      // and a bin at most 32768 in total, so neither half overflows.
+      const uint32_t inc = (q & 1) ? 0x10000u : 1u;
       if (fast) {
         const uint32_t qbytes = chunk_len >> 2;  // bytes of input per stream quarter
         const uint4* src = reinterpret_cast<const uint4*>(in_c + (uint64_t)q * qbytes);
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
                   const int sh = 8 * b - kShift;
                   const uint32_t t = sh >= 0 ? (w[i] >> sh) : (w[i] << (-sh));
                   const uint32_t off = (t & kBinMask) | col_bytes;
-                  atomicAdd(reinterpret_cast<uint32_t*>(rep_base + ((4 * i + b) % G) * (256 * R * 4) + off), 1u);
+                  atomicAdd(reinterpret_cast<uint32_t*>(rep_base + ((4 * i + b) % G) * (256 * R * 4) + off), inc);
                 }
               }
             }
@@ -122,9 +129,10 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
           const uint32_t seg = (pl + 3) >> 2;
           const uint32_t j0 = min(pl, (uint32_t)q * seg), j1 = (q == 3) ? pl : min(pl, j0 + seg);
           for (uint32_t j = j0 + tid; j < j1; j += kEncThreads)
-            atomicAdd(&S.rep[g][rot_byte_at<G>(in_c, chunk_len, rot_words, j * G + g)][lane % R], 1u);
+            atomicAdd(&S.rep[g][rot_byte_at<G>(in_c, chunk_len, rot_words, j * G + g)][lane % R], inc);
         }
       }
+      if ((q & 1) == 0) continue;
       __syncthreads();
       // fold the columns of each bin (and clear them); thread t owns bin t of every group
       for (int g = 0; g < G; g++) {
@@ -135,7 +143,9 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
           sum += S.rep[g][tid][rr];
           S.rep[g][tid][rr] = 0;
         }
-        hist[(((uint64_t)g * K + c) * 4 + q) * 256 + tid] = (uint16_t)min(sum, 65535u);
+        uint16_t* h = hist + (((uint64_t)g * K + c) * 4 + (q - 1)) * 256 + tid;
+        h[0] = (uint16_t)(sum & 0xFFFFu);
+        h[256] = (uint16_t)(sum >> 16);
       }
       __syncthreads();
     }
