@@ -899,6 +899,13 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       // use (measured: 25 % of all stall samples on that use); across a loop back-edge it cannot,
       // so a block requested in trip k is at least one whole trip old when trip k+2 consumes it.
       const bool guard = row + 2 >= my_rows;  // look-ahead of 3 blocks: clamp in the last two rows
+      if (G > 1 && (row & (4 / kIters - 1)) == 0 && row + 8 < my_rows) {
+        // The register loads above still end up close to their first use (the rotation move), so
+        // make them L2 hits: once per 64 consumed bytes ask L2 for the line 192 bytes ahead.
+#pragma unroll
+        for (int g = 0; g < G - 1; g++)
+          if (side[g].step) asm volatile("prefetch.global.L2 [%0];" ::"l"(side[g].blk + 12));
+      }
 #pragma unroll 1
       for (int k = 0; k < kIters; k++) fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G);
     }
