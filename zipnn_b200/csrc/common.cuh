@@ -14,7 +14,7 @@ struct Ctrl {
   uint64_t total_len;    // compress: total stream length
   uint64_t group_total[4];
   uint32_t work_counter; // persistent-kernel work queue
-  uint32_t pad1;
+  uint32_t regroup_count; // decode: chunks that go through k_regroup (listed in DecodeCfg::rlist)
 };
 static_assert(sizeof(Ctrl) <= 256, "ctrl block");
 constexpr size_t kCtrlBytes = 256;

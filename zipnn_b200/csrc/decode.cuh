@@ -34,6 +34,7 @@ struct DecodeCfg {
   ItemDesc* items;      // [G*K]
   uint8_t* mode;        // [K]
   uint32_t* slot;       // [K] workspace plane slot of a general-mode chunk (G planes per slot)
+  uint32_t* rlist;      // [K] chunks that k_regroup has to write (plain and general mode), ctrl->regroup_count of them
   uint8_t* fill;        // [G*K*kFillBytes]
   uint8_t* planes;      // [slots][G][pstride]
   uint64_t pstride;
@@ -136,6 +137,7 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
       }
     }
     cfg.mode[c] = (uint8_t)m;
+    if (m == kModePlain || m == kModeGeneral) cfg.rlist[atomicAdd(&cfg.ctrl->regroup_count, 1u)] = (uint32_t)c;
   }
 }
 
@@ -790,6 +792,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
         } else {
           cfg.slot[c] = s;
           cfg.mode[c] = (uint8_t)kModeGeneral;
+          cfg.rlist[atomicAdd(&cfg.ctrl->regroup_count, 1u)] = (uint32_t)c;
         }
       }
     }
@@ -965,11 +968,10 @@ __global__ void __launch_bounds__(kMergeThreads) k_regroup(DecodeCfg cfg, uint8_
   const uint64_t K = cfg.K;
   const uint32_t chunk = cfg.chunk;
   const uint32_t tiles_per_chunk = (chunk + kMergeTile - 1) / kMergeTile;
-  const uint64_t ntiles = K * tiles_per_chunk;
+  const uint64_t ntiles = (uint64_t)cfg.ctrl->regroup_count * tiles_per_chunk;  // usually none: the fused kernel wrote everything
   for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const uint64_t c = t / tiles_per_chunk;
-    if (cfg.mode[c] == kModeFused || cfg.mode[c] == kModeSkip) continue;  // written by the fused kernel / rejected
-    const uint32_t tile = (uint32_t)(t - c * tiles_per_chunk);
+    const uint64_t c = cfg.rlist[t / tiles_per_chunk];
+    const uint32_t tile = (uint32_t)(t % tiles_per_chunk);
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)chunk) : chunk;
     const uint32_t o_begin = tile * kMergeTile;
     if (o_begin >= chunk_len) continue;

@@ -118,7 +118,7 @@ inline uint64_t num_chunks(size_t n, size_t chunk) { return (n + chunk - 1) / ch
 // ragged last chunk); the default size provides kDefaultSlots of them, the "full" size K.
 constexpr uint64_t kDefaultSlots = 64;
 struct DecWs {
-  size_t items_off, mode_off, slot_off, fill_off, planes_off, pstride, fixed;
+  size_t items_off, mode_off, slot_off, rlist_off, fill_off, planes_off, pstride, fixed;
 };
 inline DecWs dec_ws_layout(size_t orig, int G, size_t chunk) {
   DecWs L;
@@ -126,7 +126,8 @@ inline DecWs dec_ws_layout(size_t orig, int G, size_t chunk) {
   L.items_off = kCtrlBytes;
   L.mode_off = round_up(L.items_off + sizeof(ItemDesc) * (size_t)G * K, 256);
   L.slot_off = round_up(L.mode_off + K, 256);
-  L.fill_off = round_up(L.slot_off + 4 * K, 256);
+  L.rlist_off = round_up(L.slot_off + 4 * K, 256);
+  L.fill_off = round_up(L.rlist_off + 4 * K, 256);
   L.planes_off = round_up(L.fill_off + (size_t)kFillBytes * G * K, 256);
   L.pstride = round_up(chunk / (size_t)G, 16) + 16;
   L.fixed = L.planes_off + 256;
@@ -255,6 +256,7 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   cfg.items = (ItemDesc*)(ws + L.items_off);
   cfg.mode = ws + L.mode_off;
   cfg.slot = (uint32_t*)(ws + L.slot_off);
+  cfg.rlist = (uint32_t*)(ws + L.rlist_off);
   cfg.fill = ws + L.fill_off;
   cfg.planes = ws + L.planes_off;
   cfg.pstride = L.pstride;
