@@ -97,12 +97,20 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
         const uint32_t qbytes = chunk_len >> 2;  // bytes of input per stream quarter
         const uint4* src = reinterpret_cast<const uint4*>(in_c + (uint64_t)q * qbytes);
         const uint32_t nvec = qbytes >> 4;
+        // double-buffered: the next four vectors are in flight while the current four are counted
+        uint4 v[4], nv[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t u = k * kEncThreads + tid;
+          nv[k] = (u < nvec) ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+        }
         for (uint32_t u0 = 0; u0 < nvec; u0 += 4 * kEncThreads) {
-          uint4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) v[k] = nv[k];
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const uint32_t u = u0 + k * kEncThreads + tid;
-            v[k] = (u < nvec) ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+            const uint32_t u = u0 + (4 + k) * kEncThreads + tid;
+            if (u < nvec) nv[k] = __ldg(src + u);
           }
 #pragma unroll
           for (int k = 0; k < 4; k++) {

@@ -86,6 +86,8 @@ class SafeOpen:
             if pipe is not None:
                 pipe.finish()
         finally:
+            if pipe is not None:
+                pipe.release()
             if fd is not None:
                 os.close(fd)
 

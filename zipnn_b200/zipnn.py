@@ -394,6 +394,8 @@ class DecodePipe:
 
     SLAB_BYTES = 64 << 20      # pinned staging slab; a stream larger than this goes through several
     COPY_PIECE = 8 << 20       # granule handed to one worker thread
+    _shared_pool = None
+    _slab_cache = []           # pinned slabs of finished pipes, reused by the next one
 
     def __init__(self, device, streams: int = 4, stage_buffers: int = 4, copy_threads: int = 0):
         _native.require_cuda()
@@ -410,11 +412,16 @@ class DecodePipe:
         self._flags = None                 # int32[cap] on the device, one word per submitted tensor
         self._nflags = 0
         self._pending = []                 # (flag index, redo closure)
+        # pinned slabs and reader threads are process-wide: page-locking 256 MiB costs tens to hundreds
+        # of milliseconds, more than a small checkpoint takes to load
         nthreads = copy_threads or max(1, min(16, (multiprocessing.cpu_count() or 2) // 2))
-        self._pool = None
-        if nthreads > 1:
+        if nthreads > 1 and DecodePipe._shared_pool is None:
             from concurrent.futures import ThreadPoolExecutor
-            self._pool = ThreadPoolExecutor(max_workers=nthreads)
+            DecodePipe._shared_pool = ThreadPoolExecutor(max_workers=nthreads)
+        self._pool = DecodePipe._shared_pool if nthreads > 1 else None
+        for j in range(stage_buffers):
+            if DecodePipe._slab_cache:
+                self._stage[j] = DecodePipe._slab_cache.pop()
 
     # ---- host side: fill a pinned slab
     def _fill_from_host(self, dst: torch.Tensor, src: torch.Tensor):
@@ -575,10 +582,20 @@ class DecodePipe:
                 redo()
         torch.cuda.current_stream(self.device).synchronize()
 
+    def release(self):
+        """Give the pinned slabs back for the next pipe (after `finish`)."""
+        for j, evt in enumerate(self._stage_evt):
+            if evt is not None:
+                evt.synchronize()
+        for j, sl in enumerate(self._stage):
+            if sl is not None and sl.numel() == self.SLAB_BYTES and len(DecodePipe._slab_cache) < 8:
+                DecodePipe._slab_cache.append(sl)
+            self._stage[j] = None
+            self._stage_evt[j] = None
+
     def __del__(self):
         try:
-            if self._pool is not None:
-                self._pool.shutdown(wait=False)
+            self.release()
         except Exception:
             pass
 
