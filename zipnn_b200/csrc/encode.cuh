@@ -686,13 +686,15 @@ struct WbStream {
 __device__ __forceinline__ void wb_flush(uint32_t* bitbuf, WbStream& st, int lane) {
   uint32_t* gword = reinterpret_cast<uint32_t*>(st.gaddr - st.a);
   const uint32_t complete = (st.B >> 5) - st.flushed;
+  // a stream that starts in the middle of a word: bytes [a, 4) of its first word go out one by one
+  const bool split_first = (st.flushed == 0 && st.a != 0);
+  if (split_first && lane == 0 && complete > 0) {
+    const uint32_t val = bitbuf[0];
+    for (uint32_t bb = st.a; bb < 4; bb++) st.gaddr[bb - st.a] = (uint8_t)(val >> (8 * bb));
+  }
   for (uint32_t w = lane; w < complete; w += 32) {
     const uint32_t val = bitbuf[w];
-    if (st.flushed + w == 0 && st.a != 0) {
-      for (uint32_t bb = st.a; bb < 4; bb++) st.gaddr[bb - st.a] = (uint8_t)(val >> (8 * bb));
-    } else {
-      gword[st.flushed + w] = val;
-    }
+    if (!(split_first && w == 0)) gword[st.flushed + w] = val;
   }
   const uint32_t carry = bitbuf[complete];
   __syncwarp();
@@ -786,10 +788,13 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
         for (int i = 0; i < G; i++) nxt[i] = __ldg(p + i);
       }
     }
-    for (uint32_t ti = ntiles; ti-- > 0;) {
+    // Tiles run from the end of the stream to its start (huff0 emits the last symbol first); only the
+    // first one processed can be partial, so the others are compiled with `have` known to be true.
+    auto do_tile = [&](auto full_tag, const uint32_t ti) {
+      constexpr bool kFull = decltype(full_tag)::value;
       const uint32_t t0 = ti * kWbTile;
-      const uint32_t cnt = min(kWbTile, seg - t0);  // multiple of 16
-      const bool have = 16u * lane < cnt;
+      const uint32_t cnt = kFull ? kWbTile : min(kWbTile, seg - t0);  // multiple of 16
+      const bool have = kFull ? true : (16u * lane < cnt);
 #pragma unroll
       for (int i = 0; i < G; i++) cur[i] = nxt[i];
       if (ti > 0) {  // prefetch the next (lower) tile, always full
@@ -843,9 +848,16 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
               for (int i = 0; i < 4; i++) o[i] = s4 ? u[i + 1] : u[i];
               *reinterpret_cast<uint4*>(D + head + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            if ((uint32_t)lane < head) D[lane] = stg[lane];
-            const uint32_t done = head + 16 * nblk;
-            if ((uint32_t)lane < cnt - done) D[done + lane] = stg[done + lane];
+            if (kFull) {  // the 16 bytes around the 31 aligned blocks: head bytes in front, 16 - head behind
+              if (lane < 16) {
+                const uint32_t idx = (uint32_t)lane < head ? (uint32_t)lane : (kWbTile - 16u + (uint32_t)lane);
+                D[idx] = stg[idx];
+              }
+            } else {
+              if ((uint32_t)lane < head) D[lane] = stg[lane];
+              const uint32_t done = head + 16 * nblk;
+              if ((uint32_t)lane < cnt - done) D[done + lane] = stg[done + lane];
+            }
           }
           __syncwarp();
         } else if (size > 1) {
@@ -904,7 +916,9 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
           wb_flush(bitbuf, st[g], lane);
         }
       }
-    }
+        };
+    do_tile(std::false_type{}, ntiles - 1);
+    for (uint32_t ti = ntiles - 1; ti-- > 0;) do_tile(std::true_type{}, ti);
     // ---- end marks and the last partial bytes of every bitstream ----
 #pragma unroll
     for (int g = 0; g < G; g++) {
