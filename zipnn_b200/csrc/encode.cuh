@@ -836,16 +836,28 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
               const uint4 a4 = *reinterpret_cast<const uint4*>(stg + 16 * lane);
               const uint4 b4 = *reinterpret_cast<const uint4*>(stg + 16 * lane + 16);
               const uint32_t wv[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+              // 16 bytes starting `head` bytes into (a4, b4): the word part of the shift is uniform over
+              // the warp, so it is a 4-way switch (4 funnel shifts) rather than 7 shifts + 9 selects
               const uint32_t bs = (head & 3) * 8;
-              uint32_t t[7];
+              uint32_t o[4];
+              switch (head >> 2) {
+                case 0:
 #pragma unroll
-              for (int i = 0; i < 7; i++) t[i] = __funnelshift_r(wv[i], wv[i + 1], bs);
-              const bool s4 = head & 4, s8 = head & 8;
-              uint32_t u[5], o[4];
+                  for (int i = 0; i < 4; i++) o[i] = __funnelshift_r(wv[i], wv[i + 1], bs);
+                  break;
+                case 1:
 #pragma unroll
-              for (int i = 0; i < 5; i++) u[i] = s8 ? t[i + 2] : t[i];
+                  for (int i = 0; i < 4; i++) o[i] = __funnelshift_r(wv[i + 1], wv[i + 2], bs);
+                  break;
+                case 2:
 #pragma unroll
-              for (int i = 0; i < 4; i++) o[i] = s4 ? u[i + 1] : u[i];
+                  for (int i = 0; i < 4; i++) o[i] = __funnelshift_r(wv[i + 2], wv[i + 3], bs);
+                  break;
+                default:
+#pragma unroll
+                  for (int i = 0; i < 4; i++) o[i] = __funnelshift_r(wv[i + 3], wv[i + 4], bs);
+                  break;
+              }
               *reinterpret_cast<uint4*>(D + head + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
             }
             if (kFull) {  // the 16 bytes around the 31 aligned blocks: head bytes in front, 16 - head behind
