@@ -694,13 +694,13 @@ __device__ __forceinline__ void wb_flush(uint32_t* bitbuf, WbStream& st, int lan
   }
   for (uint32_t w = lane; w < complete; w += 32) {
     const uint32_t val = bitbuf[w];
+    bitbuf[w] = 0;  // cleared as it leaves; only lane 0 touches word 0 and word `complete` below
     if (!(split_first && w == 0)) gword[st.flushed + w] = val;
   }
-  const uint32_t carry = bitbuf[complete];
-  __syncwarp();
-  for (uint32_t w = lane; w <= complete; w += 32) bitbuf[w] = 0;
-  __syncwarp();
-  if (lane == 0) bitbuf[0] = carry;
+  if (lane == 0 && complete > 0) {  // the partial word becomes word 0 of the next tile (after lane 0 cleared word 0 above)
+    bitbuf[0] = bitbuf[complete];
+    bitbuf[complete] = 0;
+  }
   st.flushed += complete;
   __syncwarp();
 }
