@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
           } else {
             const uint32_t head = 16 - m;  // bytes before the first aligned destination block
             const uint32_t nblk = (cnt - head) >> 4;
-            if ((uint32_t)lane < nblk) {
+            {  // every lane computes (the stage has 32 spare bytes behind the tile); only the store is conditional
               const uint4 a4 = *reinterpret_cast<const uint4*>(stg + 16 * lane);
               const uint4 b4 = *reinterpret_cast<const uint4*>(stg + 16 * lane + 16);
               const uint32_t wv[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(kWbWarps * 32) k_encode_write_warp(const uint8
                   for (int i = 0; i < 4; i++) o[i] = __funnelshift_r(wv[i + 3], wv[i + 4], bs);
                   break;
               }
-              *reinterpret_cast<uint4*>(D + head + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
+              if ((uint32_t)lane < nblk) *reinterpret_cast<uint4*>(D + head + 16 * lane) = make_uint4(o[0], o[1], o[2], o[3]);
             }
             if (kFull) {  // the 16 bytes around the 31 aligned blocks: head bytes in front, 16 - head behind
               if (lane < 16) {
