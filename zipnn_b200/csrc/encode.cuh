@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
 // pass A2: one warp per (group, chunk) item: everything the reference does per block after
 // the histogram (huf_compress.c:671-724 + csrc/zipnn_core.c:371-385).
 // =====================================================================================
+constexpr uint64_t kScanItems = 2048;  // chunks of one group per k_encode_scan CTA
+
 struct __align__(16) TableWarp {
   uint16_t hist[4][256];
   uint32_t total[256];
@@ -284,7 +286,7 @@ __device__ void warp_block_decision(TableWarp& S, uint32_t plen, double thr, uin
 template <int G>
 __global__ void __launch_bounds__(kTableWarps * 32) k_encode_table(const uint16_t* __restrict__ hist, uint64_t n, uint32_t chunk,
                                                                    uint64_t K, double thr, uint8_t* types, uint32_t* sizes,
-                                                                   EncSave* saves) {
+                                                                   EncSave* saves, unsigned long long* partials) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TableWarp& S = reinterpret_cast<TableWarp*>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
@@ -301,64 +303,100 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_encode_table(const uint16_
     __syncwarp();
     warp_block_decision(S, plane_len(chunk_len, G, g), thr, types + item, sizes + item, saves + item);
     __syncwarp();
+    // payload bytes of this group per block of kScanItems chunks: lets the scan run on many CTAs
+    if (lane == 0) atomicAdd(partials + (uint64_t)g * ((K + kScanItems - 1) / kScanItems) + c / kScanItems, (unsigned long long)sizes[item]);
   }
 }
 
 // =====================================================================================
 // scan: sizes -> cumulative table (written into the stream), bases, item offsets, header.
 // =====================================================================================
-constexpr int kScanThreads = 1024;
+constexpr int kScanThreads = 256;
+// (kScanItems = kScanThreads * 8 chunks of one group per CTA, declared above k_encode_table)
 
+// One CTA per (group, block of kScanItems chunks).  The table kernel left the payload bytes of every
+// such block in partials[g][blk]; a CTA adds up what lies in front of it (all blocks of the groups
+// before, the earlier blocks of its own group), scans its own 2048 sizes (8 per thread) and writes its
+// slice of the cumulative table, the item offsets and the type bytes.  CTA 0 also writes the header.
 __global__ void __launch_bounds__(kScanThreads) k_encode_scan(const uint32_t* __restrict__ sizes, const uint8_t* __restrict__ types,
                                                               int G, uint64_t K, const uint8_t* __restrict__ hdr_dev,
-                                                              uint32_t hdr_len, uint8_t* out, uint64_t* item_off, Ctrl* ctrl) {
-  __shared__ uint64_t warp_tot[32];
-  __shared__ uint64_t carry_s;
+                                                              uint32_t hdr_len, uint8_t* out, uint64_t* item_off, Ctrl* ctrl,
+                                                              const unsigned long long* __restrict__ partials) {
+  __shared__ uint64_t warp_tot[kScanThreads / 32];
+  __shared__ uint64_t red[kScanThreads / 32][3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t nitems = (uint64_t)G * K;
-  uint8_t* cum_out = out + hdr_len + nitems;
-  const uint64_t payload0 = (uint64_t)hdr_len + 9 * nitems;
-  uint64_t base = payload0;
-  for (uint64_t i = tid; i < nitems; i += kScanThreads) out[hdr_len + i] = types[i];
-  for (int g = 0; g < G; g++) {
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (uint64_t c0 = 0; c0 < K; c0 += kScanThreads) {
-      const uint64_t c = c0 + tid;
-      const uint64_t v = (c < K) ? sizes[(uint64_t)g * K + c] : 0;
-      uint64_t x = v;
+  const uint64_t nblk = (K + kScanItems - 1) / kScanItems;
+  const int g = (int)(blockIdx.x / nblk);
+  const uint64_t blk = blockIdx.x - (uint64_t)g * nblk;
+  // ---- what lies in front of this CTA: whole earlier groups, earlier blocks of this group, everything
+  uint64_t s_groups = 0, s_blocks = 0, s_all = 0;
+  for (uint64_t i = tid; i < (uint64_t)G * nblk; i += kScanThreads) {
+    const uint64_t v = partials[i];
+    const uint64_t gi = i / nblk;
+    s_all += v;
+    if (gi < (uint64_t)g) s_groups += v;
+    if (gi == (uint64_t)g && i - gi * nblk < blk) s_blocks += v;
+  }
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      if (lane == 31) warp_tot[warp] = x;
-      __syncthreads();
-      uint64_t pre = carry_s;
-      for (int w = 0; w < warp; w++) pre += warp_tot[w];
-      const uint64_t incl = pre + x;
-      if (c < K) {
-        st_u64_bytes(cum_out + 8 * ((uint64_t)g * K + c), incl);
-        item_off[(uint64_t)g * K + c] = base + incl - v;
-      }
-      __syncthreads();
-      if (tid == kScanThreads - 1) carry_s = incl;
-      __syncthreads();
-    }
-    if (tid == 0) {
-      ctrl->base[g] = base;
-      ctrl->group_total[g] = carry_s;
-    }
-    base += carry_s;
-    __syncthreads();
+  for (int o = 16; o; o >>= 1) {
+    s_groups += __shfl_xor_sync(0xffffffffu, s_groups, o);
+    s_blocks += __shfl_xor_sync(0xffffffffu, s_blocks, o);
+    s_all += __shfl_xor_sync(0xffffffffu, s_all, o);
   }
-  // python header with the total length patched in (csrc/zipnn_core.c:121)
-  for (uint32_t i = tid; i < hdr_len; i += kScanThreads) {
-    uint8_t b = hdr_dev[i];
-    if (i >= 24 && i < 32) b = (uint8_t)(base >> (8 * (i - 24)));
-    out[i] = b;
+  if (lane == 0) { red[warp][0] = s_groups; red[warp][1] = s_blocks; red[warp][2] = s_all; }
+  __syncthreads();
+  s_groups = s_blocks = s_all = 0;
+  for (int w = 0; w < kScanThreads / 32; w++) { s_groups += red[w][0]; s_blocks += red[w][1]; s_all += red[w][2]; }
+  const uint64_t payload0 = (uint64_t)hdr_len + 9 * nitems;
+  const uint64_t base = payload0 + s_groups;  // first payload byte of group g
+  // ---- this CTA's chunks: 8 consecutive ones per thread
+  const uint64_t c_first = blk * kScanItems + (uint64_t)tid * 8;
+  uint32_t v[8];
+  uint64_t run = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    v[j] = (c_first + j < K) ? sizes[(uint64_t)g * K + c_first + j] : 0u;
+    run += v[j];
   }
-  if (tid == 0) ctrl->total_len = base;
+  uint64_t x = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_tot[warp] = x;
+  __syncthreads();
+  uint64_t pre = s_blocks + x - run;
+  for (int w = 0; w < warp; w++) pre += warp_tot[w];
+  uint8_t* cum_out = out + hdr_len + nitems;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint64_t c = c_first + j;
+    if (c < K) {
+      const uint64_t i = (uint64_t)g * K + c;
+      item_off[i] = base + pre;
+      pre += v[j];
+      st_u64_bytes(cum_out + 8 * i, pre);  // inclusive, counted from the start of the group
+      out[hdr_len + i] = types[i];
+    }
+  }
+  if (blk == 0 && tid == 0) {
+    ctrl->base[g] = base;
+    uint64_t tot = 0;
+    for (uint64_t j = 0; j < nblk; j++) tot += partials[(uint64_t)g * nblk + j];
+    ctrl->group_total[g] = tot;
+  }
+  if (blockIdx.x == 0) {
+    // python header with the total length patched in (csrc/zipnn_core.c:121)
+    const uint64_t total = payload0 + s_all;
+    for (uint32_t i = tid; i < hdr_len; i += kScanThreads) {
+      uint8_t b = hdr_dev[i];
+      if (i >= 24 && i < 32) b = (uint8_t)(total >> (8 * (i - 24)));
+      out[i] = b;
+    }
+    if (tid == 0) ctrl->total_len = total;
+  }
 }
 
 // =====================================================================================
