@@ -395,6 +395,7 @@ class DecodePipe:
     SLAB_BYTES = 64 << 20      # pinned staging slab; a stream larger than this goes through several
     COPY_PIECE = 8 << 20       # granule handed to one worker thread
     _shared_pool = None
+    _shared_streams = {}
     _slab_cache = []           # pinned slabs of finished pipes, reused by the next one
 
     def __init__(self, device, streams: int = 4, stage_buffers: int = 4, copy_threads: int = 0):
@@ -402,7 +403,12 @@ class DecodePipe:
         self.device = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self._streams = [torch.cuda.Stream(self.device) for _ in range(streams)]
+        # side streams are process-wide per device: the caching allocator keeps one pool per stream, so a
+        # second file loaded through fresh streams would pay cudaMalloc for every tensor again
+        key = (self.device.index, streams)
+        if key not in DecodePipe._shared_streams:
+            DecodePipe._shared_streams[key] = [torch.cuda.Stream(self.device) for _ in range(streams)]
+        self._streams = DecodePipe._shared_streams[key]
         self._body = [None] * streams      # per side stream, reused in stream order
         self._ws = [None] * streams
         self._stage = [None] * stage_buffers
