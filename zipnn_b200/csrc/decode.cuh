@@ -614,13 +614,15 @@ struct FusedSmem {
   uint16_t* tail;
   uint8_t (*ring)[kRingBytes];
   uint8_t (*stage)[128];
+  uint8_t* side;   // G == 2 only: [32][64], four 16-byte slots per lane for the side plane's blocks in flight
 };
 // PB = 0: shared 256-entry u16 primaries (4 KiB); PB > 0: private u32 columns, 2^PB x 32 x 4 bytes.
 __host__ __device__ constexpr size_t fused_prim_bytes(int pb) {
   return pb == 0 ? (size_t)kDecItemsPerWarp * 512 : ((size_t)128 << pb);
 }
-__host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap, int pb) {
-  return fused_prim_bytes(pb) + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128;
+__host__ __device__ constexpr bool fused_side_in_smem(int G) { return G == 2; }
+__host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap, int pb, int G) {
+  return fused_prim_bytes(pb) + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128 + (fused_side_in_smem(G) ? 32 * 64 : 0);
 }
 __device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw, uint32_t tail_cap, int pb) {
   FusedSmem S;
@@ -629,6 +631,7 @@ __device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw, uint32
   S.tail = reinterpret_cast<uint16_t*>(raw + pbytes);
   S.ring = reinterpret_cast<uint8_t (*)[kRingBytes]>(raw + pbytes + (size_t)tail_cap * 2);
   S.stage = reinterpret_cast<uint8_t (*)[128]>(raw + pbytes + (size_t)tail_cap * 2 + 32 * kRingBytes);
+  S.side = raw + pbytes + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128;
   return S;
 }
 static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in 4 stage rows");
@@ -638,9 +641,26 @@ struct SidePlane {
   uint32_t shift;    // byte offset (0..15) of that byte inside the block
   uint32_t step;     // 1 for stream bytes, 0 for an RLE fill block
   uint4 a, b;        // blocks k, k+1
-  uint4 c, d;        // blocks k+2, k+3 in flight: two iterations of distance, because ptxas sinks a
-                     // load towards its first use and a distance of one iteration ends up as none
+  uint4 c, d;        // register path (G == 4): blocks k+2, k+3 in flight
+  uint32_t slots_s;  // smem path (G == 2): shared address of this lane's four 16-byte slots; block j waits in
+  uint32_t swz;      // slot (j & 3) ^ swz -- the XOR spreads the lanes of a quarter warp over all banks
 };
+
+// Why two paths.  A register load has a first use, and ptxas schedules the load right in front of it
+// whatever the source order says (even for ld.volatile): with the block rotation a = b, b = c, c = d
+// the first use of `d` is that move, at the end of the very iteration that requested it -- 12 % of
+// all stall samples sat on that one instruction.  cp.async has no destination register: the block
+// lands in shared memory two iterations before an LDS picks it up.  It costs 2 KiB per warp, so fp32
+// (three side planes, and secondary) keeps registers plus an L2 prefetch.
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t side_slot(const SidePlane& sp, uint32_t j) { return sp.slots_s + (((j & 3u) ^ sp.swz) << 4); }
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
 // 16 bytes starting `shift` bytes into the 32-byte pair (a, b).
@@ -685,13 +705,14 @@ __device__ __forceinline__ uint4* stage_unit(uint8_t (*stage)[128], int row, int
 // iterations of a stream can reach past it).
 template <int G, class LUT>
 __device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
-                                                const uint4* hi_block, bool guard, bool rot, uint8_t (*stage)[128], int lane, int unit0) {
+                                                const uint4* hi_block, bool guard, bool rot, uint8_t (*stage)[128], int lane, int unit0, uint32_t it) {
   if (G > 1) {
 #pragma unroll
     for (int g = 0; g < G - 1; g++) {  // block k+3 of every side plane, used two iterations later
       const uint4* nb = side[g].blk + 3 * side[g].step;
       if (guard && side[g].step && nb > hi_block) nb = hi_block;  // (an RLE fill block lives in the workspace)
-      side[g].d = ldg128(nb);
+      if (fused_side_in_smem(G)) cp_async16_s(side_slot(side[g], it + 3u), nb);  // joins the next commit group of decode16
+      else side[g].d = ldg128(nb);
     }
   }
   uint32_t pl[G][4];
@@ -729,8 +750,12 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, Si
 #pragma unroll
   for (int g = 0; g < G - 1; g++) {
     side[g].a = side[g].b;
-    side[g].b = side[g].c;
-    side[g].c = side[g].d;
+    if (fused_side_in_smem(G)) {
+      side[g].b = lds_u128(side_slot(side[g], it + 2u));  // requested in the previous iteration, landed since
+    } else {
+      side[g].b = side[g].c;
+      side[g].c = side[g].d;
+    }
     side[g].blk += side[g].step;
   }
 }
@@ -860,7 +885,13 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       const uint4* nb = side[g].blk + side[g].step;
       side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
       nb += side[g].step;
-      side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+      if (fused_side_in_smem(G)) {  // block 2 waits in slot 2 (the window setup below commits and waits for it)
+        side[g].swz = ((uint32_t)lane >> 1) & 3u;
+        side[g].slots_s = (uint32_t)__cvta_generic_to_shared(S.side) + 64u * (uint32_t)lane;
+        cp_async16_s(side_slot(side[g], 2u), (side[g].step && nb > hi_block) ? hi_block : nb);
+      } else {
+        side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+      }
     }
   }
 
@@ -896,13 +927,14 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     row_cnt[r] = __shfl_sync(0xffffffffu, my_rows, src);
   }
 
+  uint32_t it = 0;  // iterations done by this lane (side-plane slot phase)
   for (uint32_t row = 0; row < max_rows; row++) {
     if (row < my_rows) {
       // NOT unrolled: inside straight-line code ptxas sinks the side-plane loads next to their first
       // use (measured: 25 % of all stall samples on that use); across a loop back-edge it cannot,
       // so a block requested in trip k is at least one whole trip old when trip k+2 consumes it.
       const bool guard = row + 2 >= my_rows;  // look-ahead of 3 blocks: clamp in the last two rows
-      if (G > 1 && (row & (4 / kIters - 1)) == 0 && row + 8 < my_rows) {
+      if (G > 1 && !fused_side_in_smem(G) && (row & (4 / kIters - 1)) == 0 && row + 8 < my_rows) {
         // The register loads above still end up close to their first use (the rotation move), so
         // make them L2 hits: once per 64 consumed bytes ask L2 for the line 192 bytes ahead.
 #pragma unroll
@@ -910,7 +942,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
           if (side[g].step) asm volatile("prefetch.global.L2 [%0];" ::"l"(side[g].blk + 12));
       }
 #pragma unroll 1
-      for (int k = 0; k < kIters; k++) fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G);
+      for (int k = 0; k < kIters; k++) fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G, it++);
     }
     __syncwarp();
 #pragma unroll

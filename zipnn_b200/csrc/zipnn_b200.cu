@@ -287,9 +287,9 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     int rc = dispatch_G(G, [&](auto g) -> int {
       constexpr int GG = decltype(g)::value;
       if (short_codes)
-        k_huf_decode_fused<GG, 5><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 5), st>>>(cfg, (uint8_t*)d_out);
+        k_huf_decode_fused<GG, 5><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 5, GG), st>>>(cfg, (uint8_t*)d_out);
       else
-        k_huf_decode_fused<GG, 0><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 0), st>>>(cfg, (uint8_t*)d_out);
+        k_huf_decode_fused<GG, 0><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 0, GG), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });
