@@ -607,22 +607,21 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 //   ring  [32][64]       2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
 //   stage [32][128]      4 KiB   one 128-byte output row per lane, 16-byte units XOR-swizzled;
 //                                the tANS scratch of the parse aliases it (512 B per chunk)
-// Shared primaries: 11 KiB with tail_cap = 512 -> 18 warps per SM; 14 KiB with tail_cap = 2048 -> 15.
-// Private 5-bit columns (4 KiB) + tail_cap 1024: 12 KiB -> 17 warps per SM.
+//   side  [G-1][32][64]  2 KiB per side plane: blocks of the other planes in flight (cp.async)
+// bf16: private 5-bit columns (4 KiB) + tail_cap 1024 + one side plane = 14 KiB -> 15 warps per SM.
 struct FusedSmem {
   uint16_t (*prim)[256];
   uint16_t* tail;
   uint8_t (*ring)[kRingBytes];
   uint8_t (*stage)[128];
-  uint8_t* side;   // G == 2 only: [32][64], four 16-byte slots per lane for the side plane's blocks in flight
+  uint8_t* side;   // [G-1][32][64]: four 16-byte slots per lane and side plane for the blocks in flight
 };
 // PB = 0: shared 256-entry u16 primaries (4 KiB); PB > 0: private u32 columns, 2^PB x 32 x 4 bytes.
 __host__ __device__ constexpr size_t fused_prim_bytes(int pb) {
   return pb == 0 ? (size_t)kDecItemsPerWarp * 512 : ((size_t)128 << pb);
 }
-__host__ __device__ constexpr bool fused_side_in_smem(int G) { return G == 2; }
 __host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap, int pb, int G) {
-  return fused_prim_bytes(pb) + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128 + (fused_side_in_smem(G) ? 32 * 64 : 0);
+  return fused_prim_bytes(pb) + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128 + (size_t)(G - 1) * 32 * 64;
 }
 __device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw, uint32_t tail_cap, int pb) {
   FusedSmem S;
@@ -641,17 +640,18 @@ struct SidePlane {
   uint32_t shift;    // byte offset (0..15) of that byte inside the block
   uint32_t step;     // 1 for stream bytes, 0 for an RLE fill block
   uint4 a, b;        // blocks k, k+1
-  uint4 c, d;        // register path (G == 4): blocks k+2, k+3 in flight
-  uint32_t slots_s;  // smem path (G == 2): shared address of this lane's four 16-byte slots; block j waits in
+  uint32_t slots_s;  // shared address of this lane's four 16-byte slots; block j waits in
   uint32_t swz;      // slot (j & 3) ^ swz -- the XOR spreads the lanes of a quarter warp over all banks
 };
 
-// Why two paths.  A register load has a first use, and ptxas schedules the load right in front of it
-// whatever the source order says (even for ld.volatile): with the block rotation a = b, b = c, c = d
-// the first use of `d` is that move, at the end of the very iteration that requested it -- 12 % of
-// all stall samples sat on that one instruction.  cp.async has no destination register: the block
-// lands in shared memory two iterations before an LDS picks it up.  It costs 2 KiB per warp, so fp32
-// (three side planes, and secondary) keeps registers plus an L2 prefetch.
+// The blocks in flight (k+2, k+3) are NOT held in registers.  A register load has a first use, and ptxas
+// schedules the load right in front of it whatever the source order says (even for ld.volatile): with
+// a register rotation a = b, b = c, c = d the first use of `d` is that move, at the end of the very
+// iteration that requested it -- 12 % of all stall samples sat on that one instruction, and an L2
+// prefetch only shortened the wait.  cp.async has no destination register: block k+3 is requested
+// at the top of iteration k, joins the commit groups of the stream ring, and an LDS picks it up at
+// the end of iteration k+1.  64 bytes of shared memory per lane and plane.  Measured: bf16 10.43 ->
+// 9.69 ms (16 GiB), fp32 1285 -> 1456 GB/s (4 GiB).
 __device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem_src) : "memory");
 }
@@ -711,8 +711,7 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, Si
     for (int g = 0; g < G - 1; g++) {  // block k+3 of every side plane, used two iterations later
       const uint4* nb = side[g].blk + 3 * side[g].step;
       if (guard && side[g].step && nb > hi_block) nb = hi_block;  // (an RLE fill block lives in the workspace)
-      if (fused_side_in_smem(G)) cp_async16_s(side_slot(side[g], it + 3u), nb);  // joins the next commit group of decode16
-      else side[g].d = ldg128(nb);
+      cp_async16_s(side_slot(side[g], it + 3u), nb);  // joins the next commit group of decode16
     }
   }
   uint32_t pl[G][4];
@@ -750,12 +749,7 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, Si
 #pragma unroll
   for (int g = 0; g < G - 1; g++) {
     side[g].a = side[g].b;
-    if (fused_side_in_smem(G)) {
-      side[g].b = lds_u128(side_slot(side[g], it + 2u));  // requested in the previous iteration, landed since
-    } else {
-      side[g].b = side[g].c;
-      side[g].c = side[g].d;
-    }
+    side[g].b = lds_u128(side_slot(side[g], it + 2u));  // requested in the previous iteration, landed since
     side[g].blk += side[g].step;
   }
 }
@@ -885,13 +879,10 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       const uint4* nb = side[g].blk + side[g].step;
       side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
       nb += side[g].step;
-      if (fused_side_in_smem(G)) {  // block 2 waits in slot 2 (the window setup below commits and waits for it)
-        side[g].swz = ((uint32_t)lane >> 1) & 3u;
-        side[g].slots_s = (uint32_t)__cvta_generic_to_shared(S.side) + 64u * (uint32_t)lane;
-        cp_async16_s(side_slot(side[g], 2u), (side[g].step && nb > hi_block) ? hi_block : nb);
-      } else {
-        side[g].c = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
-      }
+      // block 2 waits in slot 2 (the window setup below commits and waits for it)
+      side[g].swz = ((uint32_t)lane >> 1) & 3u;
+      side[g].slots_s = (uint32_t)__cvta_generic_to_shared(S.side) + 64u * (uint32_t)(32 * g + lane);
+      cp_async16_s(side_slot(side[g], 2u), (side[g].step && nb > hi_block) ? hi_block : nb);
     }
   }
 
@@ -930,17 +921,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   uint32_t it = 0;  // iterations done by this lane (side-plane slot phase)
   for (uint32_t row = 0; row < max_rows; row++) {
     if (row < my_rows) {
-      // NOT unrolled: inside straight-line code ptxas sinks the side-plane loads next to their first
-      // use (measured: 25 % of all stall samples on that use); across a loop back-edge it cannot,
-      // so a block requested in trip k is at least one whole trip old when trip k+2 consumes it.
       const bool guard = row + 2 >= my_rows;  // look-ahead of 3 blocks: clamp in the last two rows
-      if (G > 1 && !fused_side_in_smem(G) && (row & (4 / kIters - 1)) == 0 && row + 8 < my_rows) {
-        // The register loads above still end up close to their first use (the rotation move), so
-        // make them L2 hits: once per 64 consumed bytes ask L2 for the line 192 bytes ahead.
-#pragma unroll
-        for (int g = 0; g < G - 1; g++)
-          if (side[g].step) asm volatile("prefetch.global.L2 [%0];" ::"l"(side[g].blk + 12));
-      }
 #pragma unroll 1
       for (int k = 0; k < kIters; k++) fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G, it++);
     }
