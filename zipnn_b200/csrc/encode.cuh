@@ -167,7 +167,6 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
 constexpr uint64_t kScanItems = 2048;  // chunks of one group per k_encode_scan CTA
 
 struct __align__(16) TableWarp {
-  uint16_t hist[4][256];
   uint32_t total[256];
   uint8_t nb[256];
   uint8_t nzsym[256];
@@ -175,14 +174,15 @@ struct __align__(16) TableWarp {
 };
 constexpr int kTableWarps = 4;
 
-__device__ void warp_block_decision(TableWarp& S, uint32_t plen, double thr, uint8_t* type_out, uint32_t* size_out,
-                                    EncSave* save) {
+// hist = this item's four per-stream histograms, u16[4][256] in global memory (read twice: totals, exact sizes)
+__device__ void warp_block_decision(TableWarp& S, const uint16_t* __restrict__ hist, uint32_t plen, double thr, uint8_t* type_out,
+                                    uint32_t* size_out, EncSave* save) {
   const int lane = threadIdx.x & 31;
   uint32_t* total = S.total;
   uint32_t largest = 0;
   int max_sym = -1;
   for (int s = lane; s < 256; s += 32) {
-    const uint32_t t = (uint32_t)S.hist[0][s] + S.hist[1][s] + S.hist[2][s] + S.hist[3][s];
+    const uint32_t t = (uint32_t)__ldg(hist + s) + __ldg(hist + 256 + s) + __ldg(hist + 512 + s) + __ldg(hist + 768 + s);
     total[s] = t;
     largest = max(largest, t);
     if (t) max_sym = s;
@@ -250,7 +250,7 @@ __device__ void warp_block_decision(TableWarp& S, uint32_t plen, double thr, uin
       for (int s = lane; s <= max_sym; s += 32) {
         const uint32_t l = S.nb[s];
 #pragma unroll
-        for (int q = 0; q < 4; q++) bits[q] += (uint32_t)S.hist[q][s] * l;
+        for (int q = 0; q < 4; q++) bits[q] += (uint32_t)__ldg(hist + 256 * q + s) * l;
       }
 #pragma unroll
       for (int q = 0; q < 4; q++)
@@ -296,12 +296,7 @@ __global__ void __launch_bounds__(kTableWarps * 32) k_encode_table(const uint16_
     const int g = (int)(item / K);
     const uint64_t c = item - (uint64_t)g * K;
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(n - c * (uint64_t)chunk) : chunk;
-    const uint4* src = reinterpret_cast<const uint4*>(hist + item * 1024);
-    uint4* dst = reinterpret_cast<uint4*>(&S.hist[0][0]);
-#pragma unroll
-    for (int i = 0; i < 4; i++) dst[lane + 32 * i] = __ldg(src + lane + 32 * i);
-    __syncwarp();
-    warp_block_decision(S, plane_len(chunk_len, G, g), thr, types + item, sizes + item, saves + item);
+    warp_block_decision(S, hist + item * 1024, plane_len(chunk_len, G, g), thr, types + item, sizes + item, saves + item);
     __syncwarp();
     // payload bytes of this group per block of kScanItems chunks: lets the scan run on many CTAs
     if (lane == 0) atomicAdd(partials + (uint64_t)g * ((K + kScanItems - 1) / kScanItems) + c / kScanItems, (unsigned long long)sizes[item]);
