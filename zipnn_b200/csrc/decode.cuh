@@ -918,12 +918,14 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     row_cnt[r] = __shfl_sync(0xffffffffu, my_rows, src);
   }
 
-  uint32_t it = 0;  // iterations done by this lane (side-plane slot phase)
   for (uint32_t row = 0; row < max_rows; row++) {
     if (row < my_rows) {
       const bool guard = row + 2 >= my_rows;  // look-ahead of 3 blocks: clamp in the last two rows
-#pragma unroll 1
-      for (int k = 0; k < kIters; k++) fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G, it++);
+      // unrolled: with it = row * kIters + k the slot phases (it + 2) & 3, (it + 3) & 3 fold to constants for
+      // the 16-bit types (kIters = 4)
+#pragma unroll
+      for (int k = 0; k < kIters; k++)
+        fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G, row * (uint32_t)kIters + (uint32_t)k);
     }
     __syncwarp();
 #pragma unroll
