@@ -182,13 +182,13 @@ __device__ __forceinline__ void cp_async_wait() {
 // ring's offset space) and a count `c` of bits already consumed from its top, as in
 // bitstream.h:272-443, but refilled one aligned 32-bit word at a time: when 32 or more bits are
 // gone, cont = cont << 32 | next, where `next` (the word below q) was read from the ring at the
-// PREVIOUS refill.  A symbol costs peek = (cont << c) >> 53 and c += length; the refill check runs
+// PREVIOUS refill.  A symbol costs peek = cont >> (53 - c) and c += length; the refill check runs
 // every 2 symbols (31 + 2 x 11 <= 64 - 11).  The shared-memory read is off the dependent chain
 // (its result is needed one refill later) and happens once per 32 stream bits instead of three
 // times per 4 symbols.
 struct BitWindow {
   uint64_t cont;         // bytes [q, q+8) of the stream, little endian
-  uint32_t c;            // bits consumed from the top of `cont`
+  int32_t s;             // 53 - (bits consumed from the top of `cont`): (uint32_t)(cont >> s) has the next 11 bits in [10:0]
   uint32_t q;            // byte offset (from gbase) of the container's lowest byte; moves down by 4
   uint32_t next;         // the word at q - 4
   uint32_t rd;           // shared-space address of the word at q - 8 (read by the next refill)
@@ -224,9 +224,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   return v;
 }
 __device__ __forceinline__ void window_refill(BitWindow& b) {
-  if (b.c >= 32u) {
+  if (b.s <= 21) {  // 32 or more bits consumed
     b.cont = (b.cont << 32) | b.next;
-    b.c -= 32u;
+    b.s += 32;
     b.q -= 4u;
     b.next = lds_u32(b.rd);
     b.rd = b.ring_s | ((b.rd - 4u) & (kRingBytes - 4u));
@@ -247,7 +247,7 @@ __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint
   if (mark == b.start_bit) return false;
   const uint32_t top_byte = (mark - 1) >> 3;
   b.q = (top_byte & ~3u) - 4u;
-  b.c = 8u * (b.q + 8u) - mark;  // 1..32 bits above the first unread bit
+  b.s = 53 - (int32_t)(8u * (b.q + 8u) - mark);  // 1..32 bits lie above the first unread bit
   b.fetch = (top_byte & ~15u) + 16;
   ring_top_up(b, (int)(kRingBytes / 16));
   cp_async_commit();
@@ -260,7 +260,7 @@ __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint
 }
 
 __device__ __forceinline__ bool window_exact(const BitWindow& b) {
-  return 8u * (b.q + 8u) - b.c == b.start_bit;  // every bit down to the stream start consumed, none below
+  return 8u * (b.q + 8u) - (uint32_t)(53 - b.s) == b.start_bit;  // every bit down to the stream start consumed, none below
 }
 
 // ---- decode tables ------------------------------------------------------------------
@@ -268,7 +268,9 @@ __device__ __forceinline__ bool window_exact(const BitWindow& b) {
 struct LutFull {
   const uint16_t* lut;
   int lg;
-  __device__ __forceinline__ uint32_t get(uint32_t top32) const { return lut[top32 >> (32 - lg)]; }
+  __device__ __forceinline__ int32_t get(uint32_t x) const {
+    return (int32_t)reinterpret_cast<const int16_t*>(lut)[(x & 0x7FFu) >> (11 - lg)];
+  }
 };
 // Two-level table in an 11-bit index space (shorter table logs are replicated into it):
 // codes of <= 8 bits resolve in a 256-entry primary indexed by the top 8 bits; longer codes
@@ -280,38 +282,42 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
   asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ int32_t lds_s16(uint32_t saddr) {
+  int32_t v;  // sign-extended: byte 1 of an entry is minus the code length
+  asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 struct LutTwo {
   uint32_t prim_s;  // shared-space byte address of the 256-entry primary
   uint32_t tail_s;  // ... of the x_long-entry tail (32-bit shared addresses: a generic pointer makes
                     // the compiler rebuild the shared window base for every lookup)
   uint32_t x_long;
-  __device__ __forceinline__ uint32_t get(uint32_t top32) const {
-    const uint32_t idx = top32 >> 21;
-    uint32_t k;  // opaque shift: otherwise the address becomes shift + mask + add instead of shift + IADD3
-    asm("shr.u32 %0, %1, 24;" : "=r"(k) : "r"(top32));
-    uint32_t e = lds_u16(prim_s + k + k);
-    if (idx < x_long) e = lds_u16(tail_s + idx + idx);
+  __device__ __forceinline__ int32_t get(uint32_t x) const {
+    const uint32_t idx = x & 0x7FFu;
+    int32_t e = lds_s16(prim_s + ((x >> 2) & 0x1FEu));  // 2 * (top 8 of the 11 bits)
+    if (idx < x_long) e = lds_s16(tail_s + idx + idx);
     return e;
   }
 };
 
 // Private-column table for planes with short codes (the exponent plane of bf16 / fp32: 98 % of the
-// symbols have codes of <= 6 bits).  The shared 256-entry primary above is read at random words by
+// symbols have codes of <= 5 bits).  The shared 256-entry primary above is read at random words by
 // 32 lanes: ~3.5 bank conflicts per lookup, and the LSU pipe becomes the limit of the whole kernel.
-// Here every lane owns one 4-byte bank column: entry k of lane L is word [k][L] of a [2^PB][32] u32
-// array, indexed by the top PB window bits -- conflict-free by construction.  Codes longer than PB
-// bits resolve in the shared tail (index < x_long), which few lanes touch.
+// Here every lane owns a column of a [32][32] u16 array indexed by the top 5 window bits (two lanes
+// share a 4-byte bank word, which is not a conflict), 2 KiB per warp.  The array is 2 KiB ALIGNED in
+// the shared address space, so that (x & 0x7C0) | column address is the entry's address in ONE LOP3:
+// row stride 64 bytes = bit 6, the 5 index bits are x[10:6].  Codes longer than 5 bits resolve in
+// the shared tail (index < x_long), which few lanes touch.
 template <int PB>
 struct LutCol {
-  uint32_t col_s;   // shared-space address of this lane's column (entry 0)
+  static_assert(PB == 5, "the one-instruction address needs 2^(11-PB) = 64 bytes = one row of 32 u16");
+  uint32_t col_s;   // shared-space address of this lane's entry 0 (2 KiB aligned array + 2 * lane)
   uint32_t tail_s;
   uint32_t x_long;
-  __device__ __forceinline__ uint32_t get(uint32_t top32) const {
-    const uint32_t idx = top32 >> 21;
-    uint32_t k;
-    asm("shr.u32 %0, %1, %2;" : "=r"(k) : "r"(top32), "n"(32 - PB));
-    uint32_t e = lds_u32(col_s + (k << 7));
-    if (idx < x_long) e = lds_u16(tail_s + idx + idx);
+  __device__ __forceinline__ int32_t get(uint32_t x) const {
+    const uint32_t idx = x & 0x7FFu;
+    int32_t e = lds_s16((x & 0x7C0u) | col_s);
+    if (idx < x_long) e = lds_s16(tail_s + idx + idx);
     return e;
   }
 };
@@ -333,7 +339,7 @@ __device__ __forceinline__ int lut_tail_size(const uint8_t* weights, int nsym, i
 
 // Fill one lane's column (all 4 lanes of a chunk run it) and, when `with_tail`, the chunk's tail.
 template <int PB>
-__device__ __forceinline__ void fill_lut_col(uint32_t* col /* entry k at col[32 * k] */, uint16_t* tail, bool with_tail,
+__device__ __forceinline__ void fill_lut_col(uint16_t* col /* entry k at col[32 * k] */, uint16_t* tail, bool with_tail,
                                              const uint8_t* weights, int nsym, int lg) {
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
@@ -352,7 +358,7 @@ __device__ __forceinline__ void fill_lut_col(uint32_t* col /* entry k at col[32 
     if (w == 0) continue;
     const int len = lg + 1 - w;
     const uint32_t span = 1u << (kDecLutLog - len);
-    const uint32_t e = (uint32_t)n | ((uint32_t)len << 8);
+    const uint32_t e = (uint32_t)n | (((256u - (uint32_t)len) & 0xFFu) << 8);  // symbol | -length
     const uint32_t u = start[w];
     start[w] = u + span;
     if (len > PB) {
@@ -360,17 +366,22 @@ __device__ __forceinline__ void fill_lut_col(uint32_t* col /* entry k at col[32 
         for (uint32_t q = 0; q < span; q++) tail[u + q] = (uint16_t)e;
     } else {
       const uint32_t p0 = u >> (kDecLutLog - PB), pn = span >> (kDecLutLog - PB);
-      for (uint32_t q = 0; q < pn; q++) col[32 * (p0 + q)] = e;
+      for (uint32_t q = 0; q < pn; q++) col[32 * (p0 + q)] = (uint16_t)e;
     }
   }
 }
 
+// Table entries are 16 bits: symbol in byte 0, MINUS the code length in byte 1 (two's complement), read
+// with a sign-extending load.  With s = 53 - consumed the dependent chain per symbol is
+//   SHF.R.U64 (cont >> s)  ->  LOP3 (table address)  ->  LDS.S16  ->  LEA.HI.SX32 (s += e >> 8)
+// three ALU operations and the load; the straightforward (cont << c) >> 32, index, address, c += len
+// takes four.
 template <class LUT>
 __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) {
-  const uint32_t top32 = (uint32_t)((b.cont << b.c) >> 32);
-  const uint32_t e = lut.get(top32);
-  b.c += e >> 8;
-  return e;  // symbol in byte 0, length in byte 1
+  const uint32_t x = (uint32_t)(b.cont >> b.s);  // next 11 stream bits in [10:0], later bits below... above them: older bits
+  const int32_t e = lut.get(x);
+  b.s += e >> 8;  // s -= length
+  return (uint32_t)e;  // symbol in byte 0
 }
 
 // 16 symbols -> 4 words (symbol j in byte j).  Ring maintenance for the NEXT iterations is
@@ -423,7 +434,7 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
     const int w = weights[n];
     if (w == 0) continue;
     const uint32_t len = 1u << (w - 1);
-    const uint16_t e = (uint16_t)(n | ((lg + 1 - w) << 8));
+    const uint16_t e = (uint16_t)(n | (((256 - (lg + 1 - w)) & 0xFF) << 8));  // symbol | -length
     uint32_t u = start[w];
     start[w] = u + len;
     if (len >= 4 && (u & 1) == 0) {
@@ -471,7 +482,7 @@ __device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const 
     if (w == 0) continue;
     const int len = lg + 1 - w;
     const uint32_t span = 1u << (kDecLutLog - len);
-    const uint16_t e = (uint16_t)(n | (len << 8));
+    const uint16_t e = (uint16_t)(n | (((256 - len) & 0xFF) << 8));  // symbol | -length
     const uint32_t u = start[w];
     start[w] = u + span;
     if (len > 8) {
@@ -548,7 +559,7 @@ __device__ __forceinline__ bool setup_item(DecodeSmem& S, const uint8_t* body, c
 // Kernel 2a: general mode -- decode coded planes into workspace planes.
 // ====================================================================================
 __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t nitems = (uint64_t)cfg.G * cfg.K;
@@ -616,10 +627,10 @@ struct FusedSmem {
   uint8_t (*stage)[128];
   uint8_t* side;   // [G-1][32][64]: four 16-byte slots per lane and side plane for the blocks in flight
 };
-// PB = 0: shared 256-entry u16 primaries (4 KiB); PB > 0: private u32 columns, 2^PB x 32 x 4 bytes.
-__host__ __device__ constexpr size_t fused_prim_bytes(int pb) {
-  return pb == 0 ? (size_t)kDecItemsPerWarp * 512 : ((size_t)128 << pb);
-}
+// PB = 0: shared 256-entry u16 primaries (4 KiB).  PB = 5: private u16 columns, 2 KiB, which must start
+// on a 2 KiB boundary of the shared address space (LutCol); the dynamic buffer is 1 KiB aligned, so the
+// area is 3 KiB and the columns start 0 or 1 KiB into it.
+__host__ __device__ constexpr size_t fused_prim_bytes(int pb) { return pb == 0 ? (size_t)kDecItemsPerWarp * 512 : (size_t)3072; }
 __host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap, int pb, int G) {
   return fused_prim_bytes(pb) + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128 + (size_t)(G - 1) * 32 * 64;
 }
@@ -756,14 +767,20 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, Si
 
 template <int G, int PB>
 __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const FusedSmem S = fused_smem_carve(smem_raw, cfg.tail_cap, PB);
-  using LUT = typename std::conditional<PB == 0, LutTwo, LutCol<(PB ? PB : 1)>>::type;
+  using LUT = typename std::conditional<PB == 0, LutTwo, LutCol<(PB ? PB : 5)>>::type;
+  // private columns: first 2 KiB boundary of the shared address space inside the 3 KiB table area
+  const uint32_t col_off = PB ? ((2048u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 2047u)) & 2047u) : 0u;
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t K = cfg.K;
   const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
   const bool active = (c < K) && cfg.mode[c] == kModeFused;
   if (__ballot_sync(0xffffffffu, active) == 0) return;
+  if (PB != 0 && col_off > 1024u) {  // the dynamic buffer is not 1 KiB aligned: cannot happen, but never decode wrongly
+    if (lane == 0) atomicOr(&cfg.ctrl->error, kErrUnsupported);
+    return;
+  }
 
   ItemDesc d;  // the coded plane: always group G-1 in fused mode
   d.kind = kRaw;
@@ -823,7 +840,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     if (PB != 0) {  // private columns: the 4 lanes of a chunk fill their own copy in parallel
       nsym = __shfl_sync(0xffffffffu, nsym, lane & ~3);
       if (active && hsize >= 0)
-        fill_lut_col<(PB ? PB : 1)>(reinterpret_cast<uint32_t*>(smem_raw) + lane, S.tail + tail_at, stream == 0, weights, nsym, lg);
+        fill_lut_col<(PB ? PB : 5)>(reinterpret_cast<uint16_t*>(smem_raw + col_off) + lane, S.tail + tail_at, stream == 0, weights, nsym, lg);
     }
     __syncwarp();  // the ring and the stage (aliased by the parse scratch) are free from here on
   }
@@ -891,7 +908,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
   if constexpr (PB == 0) {
     lut.prim_s = (uint32_t)__cvta_generic_to_shared(S.prim[slot]);
   } else {
-    lut.col_s = (uint32_t)__cvta_generic_to_shared(smem_raw) + 4u * (uint32_t)lane;
+    lut.col_s = (uint32_t)__cvta_generic_to_shared(smem_raw) + col_off + 2u * (uint32_t)lane;
   }
   lut.tail_s = (uint32_t)__cvta_generic_to_shared(S.tail + tail_at);
   lut.x_long = (uint32_t)x_long;

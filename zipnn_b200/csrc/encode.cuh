@@ -73,7 +73,7 @@ struct HistSmem {
 template <int G>
 __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __restrict__ in, uint64_t n, uint32_t chunk,
                                                              uint64_t K, int bits_mode, uint16_t* __restrict__ hist) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   HistSmem<G>& S = *reinterpret_cast<HistSmem<G>*>(smem_raw);
   constexpr int R = HistCfg<G>::R;
   constexpr int kShift = HistCfg<G>::kShift;
@@ -287,7 +287,7 @@ template <int G>
 __global__ void __launch_bounds__(kTableWarps * 32) k_encode_table(const uint16_t* __restrict__ hist, uint64_t n, uint32_t chunk,
                                                                    uint64_t K, double thr, uint8_t* types, uint32_t* sizes,
                                                                    EncSave* saves, unsigned long long* partials) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   TableWarp& S = reinterpret_cast<TableWarp*>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const uint64_t nitems = (uint64_t)G * K;
