@@ -294,7 +294,7 @@ struct LutTwo {
   uint32_t x_long;
   __device__ __forceinline__ int32_t get(uint32_t x) const {
     const uint32_t idx = x & 0x7FFu;
-    int32_t e = lds_s16(prim_s + ((x >> 2) & 0x1FEu));  // 2 * (top 8 of the 11 bits)
+    int32_t e = lds_s16(((x >> 2) & 0x1FEu) | prim_s);  // 2 * (top 8 of the 11 bits); every primary is 512-byte aligned
     if (idx < x_long) e = lds_s16(tail_s + idx + idx);
     return e;
   }
