@@ -612,14 +612,15 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
 // Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
 // ====================================================================================
 // Shared memory of one warp (dynamic, tail_cap is a launch parameter):
-//   prim  [8][256] u16   4 KiB   primary tables
+//   prim  [8][256] u16   4 KiB   shared primary tables (PB = 0), or 3 KiB holding [32][32] u16 private columns (PB = 5)
 //   tail  [tail_cap] u16         tail tables of the 8 chunks packed back to back (bf16 / fp32
 //                                exponent planes need ~16 entries each, fp16 ~90, fp8 ~150)
 //   ring  [32][64]       2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
 //   stage [32][128]      4 KiB   one 128-byte output row per lane, 16-byte units XOR-swizzled;
 //                                the tANS scratch of the parse aliases it (512 B per chunk)
 //   side  [G-1][32][64]  2 KiB per side plane: blocks of the other planes in flight (cp.async)
-// bf16: private 5-bit columns (4 KiB) + tail_cap 1024 + one side plane = 14 KiB -> 15 warps per SM.
+// bf16: 3 KiB table area (2 KiB of private 5-bit u16 columns) + tail_cap 1024 + one side plane = 13 KiB
+// -> 16 warps per SM.
 struct FusedSmem {
   uint16_t (*prim)[256];
   uint16_t* tail;

@@ -276,11 +276,10 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     const uint64_t warps = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
     if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
     // Short-code planes (the exponent plane of the rotated types, ~2.6 bits per symbol) use
-    // conflict-free private 5-bit table columns (4 KiB) and a 1024-entry tail pool (8 chunks x
-    // ~64-100 entries for the codes longer than 5 bits): 12 KiB per warp, 17 warps per SM.
-    // Measured on 16 GiB bf16: 4 or 5 bits 10.9 ms, 6 bits 11.3, 7 bits (9 warps) 13.4, shared
-    // 8-bit primaries 11.5.  fp16 / fp8 planes (6-7 bits per symbol, 90-150 entries of > 8 bits per
-    // chunk) keep the shared 8-bit primaries.  A chunk whose tail does not fit takes the general path.
+    // conflict-free private 5-bit table columns and a 1024-entry tail pool (8 chunks x ~64 entries
+    // for the codes longer than 5 bits, so 2x slack): 13 KiB per warp with one side plane, 16 warps
+    // per SM.  fp16 / fp8 planes (6-7 bits per symbol, 90-150 entries of > 8 bits per chunk) keep the
+    // shared 8-bit primaries.  A chunk whose tail does not fit the pool takes the general path.
     const bool short_codes = (G >= 2 && bits_mode == 1);
     cfg.tail_cap = short_codes ? 1024u : 2048u;
     ScopedTimer tm(kKHufDecode, st);
