@@ -758,6 +758,13 @@ def _compress_host_pipelined(src: torch.Tensor, header: bytes, G: int, bits_mode
     cum_all = np.empty((G, K), dtype=np.int64)
     run = np.zeros(G, dtype=np.int64)              # bytes of each group in the slabs before this one
     slab_off = []                                  # per slab: payload offset inside `held` of each group, sizes
+    # Groups behind group 0 leave early too, on the bet that every group in front of them stays raw
+    # (the mantissa planes of float weights always do): then their base is known in advance.  A lost
+    # bet costs one more copy of that group at the end.
+    pred_tot = np.array([n // G + (1 if g < n % G else 0) for g in range(G)], dtype=np.int64)
+    pred_base = payload0 + np.concatenate([[0], np.cumsum(pred_tot)[:-1]])
+    all_raw = np.ones(G, dtype=bool)
+    early = [False] * G                            # group g was (so far) copied out at pred_base[g]
     for st in streams:
         st.wait_stream(cur)
     out_stream.wait_stream(cur)
@@ -790,12 +797,22 @@ def _compress_host_pipelined(src: torch.Tensor, header: bytes, G: int, bits_mode
         if 32 + 9 * G * Ks + int(tot.sum()) != out_len.value:
             raise RuntimeError("zipnn_b200: inconsistent slab stream")
         slab_off.append((offs, tot, run.copy()))
-        if tot[0]:
-            with torch.cuda.stream(out_stream):
-                a = payload0 + int(run[0])
-                if a + int(tot[0]) > cap:
-                    raise ValueError("out= must be a contiguous CPU tensor with room for the result")
-                host[a: a + int(tot[0])].copy_(dst[int(offs[0]): int(offs[0]) + int(tot[0])], non_blocking=True)
+        all_raw &= ~np.any(types_all[:, c0:c1] != 0, axis=1)
+        with torch.cuda.stream(out_stream):
+            for g in range(G):
+                if g and not bool(np.all(all_raw[:g])):
+                    early[g] = False
+                    continue
+                a = int(pred_base[g] + run[g])             # exact for group 0, a bet for the others
+                if a + int(tot[g]) > cap:
+                    if g == 0:
+                        raise ValueError("out= must be a contiguous CPU tensor with room for the result")
+                    early[g] = False
+                    continue
+                if i == 0:
+                    early[g] = True
+                if tot[g] and (g == 0 or early[g]):
+                    host[a: a + int(tot[g])].copy_(dst[int(offs[g]): int(offs[g]) + int(tot[g])], non_blocking=True)
         run += tot
     base = payload0 + np.concatenate([[0], np.cumsum(run)[:-1]])
     total = payload0 + int(run.sum())
@@ -803,6 +820,8 @@ def _compress_host_pipelined(src: torch.Tensor, header: bytes, G: int, bits_mode
         raise ValueError("out= must be a contiguous CPU tensor with room for the result")
     with torch.cuda.stream(out_stream):
         for g in range(1, G):
+            if early[g] and int(base[g]) == int(pred_base[g]):
+                continue                                   # already in place
             for i in range(len(slabs)):
                 offs, tot, before = slab_off[i]
                 if tot[g]:
