@@ -148,3 +148,23 @@ def test_gpu_load_path_many_tensors_and_deferred_errors(tmp_path):
         with SafeOpen(str(bad), "pt", "cuda") as f:
             for k in f.keys():
                 f.get_tensor(k)
+
+
+def test_safetensors_index_matches_the_library(tmp_path):
+    """The GPU load path reads compressed entries straight from the file: its own index of
+    (offset, length) must address exactly the bytes safetensors hands out."""
+    from safetensors.torch import save_file as sf
+    from zipnn_b200.safetensors_io import _safetensors_index
+    tensors = {"a": torch.arange(1000, dtype=torch.int32), "b": (torch.randn(77, 3) * 0.02).to(torch.bfloat16),
+               "c": torch.zeros(0, dtype=torch.float32), "d": torch.randint(0, 255, (4097,), dtype=torch.uint8)}
+    path = tmp_path / "idx.safetensors"
+    sf(tensors, str(path), {"k": "v"})
+    idx = _safetensors_index(str(path))
+    blob = open(path, "rb").read()
+    assert set(idx) == set(tensors)
+    with safe_open(str(path), "pt", "cpu") as f:
+        for name in f.keys():
+            off, n = idx[name]
+            t = f.get_tensor(name)
+            assert n == t.numel() * t.element_size()
+            assert blob[off: off + n] == t.contiguous().view(torch.uint8).numpy().tobytes(), name

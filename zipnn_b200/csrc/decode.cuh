@@ -277,11 +277,6 @@ struct LutFull {
 // sit at the bottom of the canonical order (index < x_long) and resolve in a tail table
 // indexed by all 11 bits (read only by the lanes that need it).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
-__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
-  uint32_t v;  // zero-extended; plain asm (not volatile) so the compiler may schedule and predicate it
-  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
 __device__ __forceinline__ int32_t lds_s16(uint32_t saddr) {
   int32_t v;  // sign-extended: byte 1 of an entry is minus the code length
   asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(saddr));
