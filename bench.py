@@ -119,18 +119,36 @@ def make_tensor(nbytes, dtype, device, seed):
 
 
 def cpu_reference_codec():
-    """-> (kind, compress(bytes, threads) -> stream, decompress(stream, n, threads))."""
+    """-> (kind, compress(bytes, threads) -> stream, decompress(stream, n, threads), release(buffer))."""
     from oracle import oracle as O
     ref = O.ref_core()
     hdr = bytearray(32)
     hdr[0:2] = b"ZN"
     if ref is not None:
+        import ctypes
+        import numpy as np
+        libc_free = ctypes.CDLL(None).free
+        libc_free.argtypes = [ctypes.c_void_p]
+        libc_free.restype = None
+
         def comp(buf, th):
             return ref.zipnn_core(bytes(hdr), buf, 2, 1, 10, 0, 262144, 0.95, 10, th)
 
         def dec(stream, n, th):
             return ref.combine_dtype(memoryview(stream)[32:], 2, 1, 10, 262144, n, th)
-        return "reference", comp, dec
+
+        def release(mv):
+            # the reference wraps a malloc'ed buffer in an owner-less memoryview (csrc/zipnn_core.c:122,594-595,
+            # 1119-1120): every call leaks its result.  The harness gives the block back (outside the timed
+            # region) so that full-size steps can repeat inside one process.
+            if mv is None or len(mv) == 0:
+                return
+            arr = np.frombuffer(mv, dtype=np.uint8)
+            addr = arr.ctypes.data
+            del arr                      # drops the buffer export, so the view can be released
+            mv.release()
+            libc_free(ctypes.c_void_p(addr))
+        return "reference", comp, dec, release
     import numpy as np
 
     def comp(buf, th):
@@ -138,14 +156,16 @@ def cpu_reference_codec():
 
     def dec(stream, n, th):
         return O.zipnn_decompress(np.asarray(stream)[32:], 2, 1, 10, 262144, n, threads=th)
-    return "port", comp, dec
+    return "port", comp, dec, (lambda mv: None)
 
 
-def time_cpu(sample_bytes, threads, reps=1):
+def time_cpu(sample_bytes, threads, reps=1, keep_stream=False):
     """Round-trip GB/s of the CPU path on `sample_bytes` (bytearray; the reference rotates it in place)."""
-    kind, comp, dec = cpu_reference_codec()
+    import numpy as np
+    kind, comp, dec, release = cpu_reference_codec()
     n = len(sample_bytes)
     best = None
+    kept = None
     for _ in range(reps):
         work = bytearray(sample_bytes)  # clone outside the timed region (SURVEY Q1)
         t0 = time.perf_counter()
@@ -155,10 +175,53 @@ def time_cpu(sample_bytes, threads, reps=1):
         t2 = time.perf_counter()
         assert len(d) == n
         cur = (t1 - t0, t2 - t1, len(s))
+        if keep_stream and kept is None:
+            kept = np.frombuffer(s, dtype=np.uint8).copy()
+        if isinstance(d, memoryview):
+            release(d)
+        if isinstance(s, memoryview):
+            release(s)
+        del work
         if best is None or cur[0] + cur[1] < best[0] + best[1]:
             best = cur
     tc, td, slen = best
-    return kind, n / (tc + td) / 1e9, n / tc / 1e9, n / td / 1e9, slen / n
+    return kind, n / (tc + td) / 1e9, n / tc / 1e9, n / td / 1e9, slen / n, kept
+
+
+def host_cpu_info():
+    """What the CPU arm can actually use on this box (explains run-to-run differences between boxes)."""
+    info = {"logical_cores": os.cpu_count()}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_" + os.path.basename(path)] = open(path).read().strip()
+            break
+        except Exception:
+            pass
+    try:
+        info["loadavg_1m"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["model"] = ln.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return info
+
+
+def workload_text(dtype_name, nbytes):
+    return (f"synthetic {dtype_name} tensor, {nbytes / GIB:.2f} GiB per GPU, randn*0.02 (seed 1234+rank), 256 KiB chunks; "
+            "step = compress the tensor + decompress the stream that came out")
+
+
+def thread_candidates(cores):
+    return sorted({t for t in (16, 32, 64, cores) if 1 <= t <= cores} | {min(16, cores)})
 
 
 # ------------------------------------------------------------------ reference arm
@@ -170,29 +233,59 @@ def run_reference(args, rank, world):
         resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
     except Exception:
         pass
+    import psutil
     import torch
     cores = os.cpu_count() or 1
-    threads = cores
-    nbytes = int(args.cpu_sample_gib * GIB)
-    t = make_tensor(nbytes, getattr(torch, args.dtype), "cpu", 1234)
-    sample = bytearray(t.view(torch.uint8).numpy().tobytes())
+    dtype = getattr(torch, args.dtype)
+    full = int(args.size_gib * GIB)
+    # the same bytes our arm codes on rank 0 (generated on the GPU when there is one: seconds instead of minutes)
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
+    avail = psutil.virtual_memory().available
+    nbytes = full
+    while nbytes > (1 << 28) and 3.2 * nbytes + (8 << 30) > avail:      # input + working clone + stream/result
+        nbytes //= 2
+    t = make_tensor(nbytes, dtype, gen_dev, 1234)
+    whole = bytearray(t.view(torch.uint8).cpu().numpy().tobytes())
+    del t
+    if gen_dev == "cuda":
+        torch.cuda.empty_cache()
+    # ---- thread sweep on a bounded sample: the reference's default (min(cpu,16), zipnn/zipnn.py:176-177) and the best of {16,32,64,all}
+    sweep_bytes = min(len(whole), 2 * GIB)
+    sweep = {}
+    for th in thread_candidates(cores):
+        _, v, vc, vd, _, _ = time_cpu(whole[:sweep_bytes], th)
+        sweep[th] = {"round_trip_gbs": round(v, 3), "compress_gbs": round(vc, 3), "decompress_gbs": round(vd, 3)}
+    best_th = max(sweep, key=lambda k: sweep[k]["round_trip_gbs"])
+    default_th = min(16, cores)
+    # ---- size of one step: the full workload unless the K + W steps would not end within a few minutes
+    budget_s = 240.0
+    sample = len(whole)
+    per_byte = 1.0 / (sweep[best_th]["round_trip_gbs"] * 1e9)
+    while sample > GIB and (args.steps + args.warmup) * sample * per_byte * 1.15 > budget_s:
+        sample //= 2
+    data = whole if sample == len(whole) else whole[:sample]
     kind = "reference"
     for _ in range(args.warmup):
-        kind, *_ = time_cpu(sample, threads)
+        kind, *_ = time_cpu(data, best_th)
     t0 = time.perf_counter()
-    vals = [time_cpu(sample, threads) for _ in range(args.steps)]
+    vals = [time_cpu(data, best_th) for _ in range(args.steps)]
     wall = time.perf_counter() - t0
     v = sum(x[1] for x in vals) / len(vals)
+    sample_txt = (f"{sample / GIB:.2f} GiB of the workload per step" + ("" if sample == full else f" (bounded: the full {full / GIB:.0f} GiB x {args.steps + args.warmup} steps would not end within {budget_s:.0f} s"
+                  + (" or does not fit host RAM" if len(whole) < full else "") + ")")
+                  + f", {best_th} threads = best of {sorted(sweep)} on a {sweep_bytes / GIB:.0f} GiB sweep; reference default is {default_th} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * nbytes / (v * 1e9), 3),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sample / (v * 1e9), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"synthetic {args.dtype} randn*0.02 tensor, 256 KiB chunks (reference arm: {args.cpu_sample_gib} GiB sample per step)",
-                   "timing": "host wall clock; the reference C path (zipnn_core.zipnn_core + combine_dtype) called directly, input clone outside the timed region"},
+        "config": {"workload": workload_text(args.dtype, full),
+                   "l2": "inputs are far larger than the 126 MB L2 (no flush needed)", "sharding": "one tensor shard per GPU, no data-path collective"},
+        "timing": "host wall clock; the reference C path (zipnn_core.zipnn_core + combine_dtype) called directly, input clone outside the timed region, leaked result buffers freed by the harness between steps",
         "compress_gbs": round(sum(x[2] for x in vals) / len(vals), 4), "decompress_gbs": round(sum(x[3] for x in vals) / len(vals), 4),
         "ratio": round(vals[0][4], 6),
-        "cpu_baseline": {"value": round(v, 4), "unit": "GB/s", "cores": threads, "kind": kind,
-                         "sample": f"{args.cpu_sample_gib} GiB of the workload per step, {threads} threads, host has {cores} logical cores"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "GB/s", "cores": best_th, "kind": kind, "sample": sample_txt,
+                         "threads_sweep": {str(k): sweep[k] for k in sorted(sweep)}, "default_threads": default_th,
+                         "default_threads_value": sweep[default_th]["round_trip_gbs"], "host": host_cpu_info()},
         "e2e": {"value": round(v, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(wall, 2),
     }
@@ -297,21 +390,71 @@ def run_ours(args, rank, local_rank, world):
                "api": "zipnn_b200.ZipNN(input_format='torch').compress(pinned cpu tensor, out=pinned) / .decompress(host stream, out=pinned): H2D copy, zipnn_b200_compress / _decompress, D2H copy"}
         del ht
 
-    # ---- CPU baseline beside it (rank 0, single-GPU runs only)
+    # ---- CPU baseline beside it (rank 0, single-GPU runs only) + stream == reference stream at the bench scale
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             import resource
             resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
         except Exception:
             pass
-        sb = int(min(args.cpu_sample_gib * GIB, nbytes))
+        import numpy as np
+        from tools.stream_windows import StreamTables, check_stream_windows
+        chunk = 262144
+        sb = int(min(args.cpu_sample_gib * GIB, nbytes)) // chunk * chunk
         sample = bytearray(t.view(torch.uint8)[:sb].cpu().numpy().tobytes())
         cores = os.cpu_count() or 1
-        kind, v, vc, vd, ratio_cpu = time_cpu(sample, cores, reps=2)
+        kind, v, vc, vd, ratio_cpu, ref_stream = time_cpu(sample, cores, reps=2, keep_stream=True)
         cpu = {"value": round(v, 4), "unit": "GB/s", "cores": cores, "kind": kind, "compress_gbs": round(vc, 4),
                "decompress_gbs": round(vd, 4), "ratio": round(ratio_cpu, 6),
                "sample": f"first {sb / GIB:.2f} GiB of the same tensor, {cores} threads (all logical cores), best of 2"}
+        # The checker's stream for the first sb bytes is a window of ours; so are the chunks whose cumulative
+        # offsets straddle 2^32 in every group (u64 size table, csrc/zipnn_core.c:145-153, 1002-1005).
+        z = ZipNN(input_format="torch")
+        gs = z.compress(t)
+        torch.cuda.synchronize()
+        hdr_len = len(z._last_plan["header"])
+        G = z._last_plan["num_buf"]
+        K = (nbytes + chunk - 1) // chunk
+        tab = StreamTables(gs, hdr_len, G, K)
+        first = True
+        _, comp, _, release = cpu_reference_codec()
+
+        def compress_window(data):
+            nonlocal first
+            if first and data.size == sb:       # the stream time_cpu kept: no second CPU pass over the first GiB
+                first = False
+                return ref_stream, 32
+            mv = comp(bytearray(data.tobytes()), cores)
+            out = np.frombuffer(mv, dtype=np.uint8).copy()
+            if isinstance(mv, memoryview):
+                release(mv)
+            return out, 32
+
+        wins = [(0, sb // chunk)]
+        for g in range(G):
+            lim = 1 << 32
+            if lim > int(tab.base[g]):
+                cx = tab.first_chunk_past(g, lim - int(tab.base[g]))   # the absolute stream offset passes 2^32 inside this group
+                if 0 < cx < K:
+                    wins.append((cx - 128, cx + 128))
+            cy = tab.first_chunk_past(g, lim)                          # the group's own cumulative size passes 2^32
+            if 0 < cy < K:
+                wins.append((cy - 128, cy + 128))
+        wins.append((K - 256, K))
+        uniq = []
+        for w in wins:
+            w = (max(0, w[0]), min(K, w[1]))
+            if w not in uniq and w[1] > w[0]:
+                uniq.append(w)
+        try:
+            res = check_stream_windows(gs, hdr_len, G, K, chunk, nbytes,
+                                       lambda a, b: t.view(torch.uint8)[a:b].cpu().numpy(), uniq, compress_window)
+            parity = {"stream_equals_reference": True, "checker": kind, "stream_bytes": int(gs.numel()), **res}
+        except AssertionError as exc:
+            parity = {"stream_equals_reference": False, "checker": kind, "error": str(exc)}
+        del gs
 
     if rank != 0:
         if world > 1:
@@ -349,8 +492,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"synthetic {args.dtype} tensor, {nbytes / GIB:.2f} GiB per GPU, randn*0.02 (seed 1234+rank), 256 KiB chunks; "
-                               "step = ZipNN.compress(cuda tensor) + ZipNN.decompress(stream), byte-exact round trip verified before timing",
+        "config": {"workload": workload_text(args.dtype, nbytes),
                    "l2": "inputs are far larger than the 126 MB L2 (no flush needed)", "sharding": "one tensor shard per GPU, no data-path collective"},
         "compress_gbs": round(world * N / (tc_ms * 1e-3) / 1e9, 2), "decompress_gbs": round(world * N / (td_ms * 1e-3) / 1e9, 2),
         "ratio": round(Cb / N, 6),
@@ -368,6 +510,8 @@ def run_ours(args, rank, local_rank, world):
         line["e2e"] = e2e
     if cpu:
         line["cpu_baseline"] = cpu
+    if parity:
+        line["parity_check"] = parity
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -55,6 +55,8 @@ CASES = [
     ("fp32_from_bf16", dict(gen="randn_bf16_as_fp32", dtype="float32", n=300000, sigma=0.02), dict(input_format="torch")),
     ("bf16_2d_shape", dict(gen="randn", dtype="bfloat16", n=70000 * 3, sigma=0.02, shape=[70000, 3]), dict(input_format="torch")),
     ("bf16_uniform", dict(gen="rand_pm1", dtype="bfloat16", n=262144 + 77, sigma=1.0), dict(input_format="torch")),
+    # ---- the 128 MiB known answer (512 chunks; stream sha 1e8d0f8b62398fb7)
+    ("bf16_128mib", dict(gen="randn", dtype="bfloat16", n=67108864, sigma=0.02), dict(input_format="torch")),
     # ---- small ones whose full stream is committed
     ("bf16_small", dict(gen="randn", dtype="bfloat16", n=40000, sigma=0.02), dict(input_format="torch")),
     ("fp16_small", dict(gen="randn", dtype="float16", n=40000, sigma=0.02), dict(input_format="torch")),
