@@ -93,6 +93,23 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
                           size_t chunk, size_t orig, void* d_out, void* d_ws, size_t ws_bytes,
                           void* cuda_stream, int check);
 
+/* ---- many tensors at once (the checkpoint load path) --------------------------------
+ * The reference decodes a safetensors file one tensor per call (zipnn/zipnn.py:1601-1607, called
+ * from vLLM's weight iterator); a GPU wants the whole shard in one go.  Every item is what one
+ * zipnn_b200_decompress call would take; all of them are decoded by ONE launch of each kernel
+ * (tensors of up to ~3000 chunks; larger ones run one by one on the same stream).
+ * Status of the whole batch: OR of the tensors' error words. */
+typedef struct zipnn_b200_batch_item {
+  const void* d_body;   /* stream after the python header, device memory */
+  size_t body_len;
+  int num_buf, bits_mode, bytes_mode;
+  size_t chunk, orig;
+  void* d_out;          /* orig bytes, 16-byte aligned */
+} zipnn_b200_batch_item;
+int zipnn_b200_decompress_batch_workspace_size(const zipnn_b200_batch_item* items, int n, size_t* out);
+int zipnn_b200_decompress_batch(const zipnn_b200_batch_item* items, int n, void* d_ws, size_t ws_bytes,
+                                void* cuda_stream, int check);
+
 /* ---- stage 1 alone ------------------------------------------------------------ */
 /* d_planes: num_buf planes of `stride` bytes each; plane g receives byte g of every element
  * of the (optionally rotated) input.  Lengths as in the reference: n/num_buf, the first

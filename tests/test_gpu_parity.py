@@ -344,3 +344,128 @@ def test_pipelined_host_compress(monkeypatch):
         assert piped == one_shot and piped_out == one_shot, str(dt)
         back = ZipNN(input_format="torch").decompress(piped)
         assert raw_bytes(back) == raw_bytes(t)
+
+
+# ------------------------------------------------------------------ round-2 paths
+def _two_coded_groups_fp32(nchunks, seed=3):
+    """fp32 values that are exact bf16 numbers: byte groups 0 and 1 are all zero (RLE), groups 2 and 3
+    are both Huffman-coded -> every chunk needs the general path (plane scratch)."""
+    g = torch.Generator().manual_seed(seed)
+    n = nchunks * 65536
+    return (torch.randn(n, generator=g) * 0.02).to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nchunks", [40, 150, 4000])
+def test_general_chunks_beyond_the_slot_pool_are_decoded_in_stream(nchunks, monkeypatch):
+    """More general-mode chunks than the default workspace has pool slots (64): the overflow kernel must
+    decode the rest in stream order -- no E_CAPACITY round trip, nothing left unwritten.
+    4000 chunks is past the sync-kernel threshold, so the one-thread-per-bitstream kernels run too."""
+    x = _two_coded_groups_fp32(nchunks)
+    raw = x.view(torch.uint8).numpy()
+    plan = ZipNN(input_format="torch").plan(x)
+    want = O.zipnn_compress(plan["header"], raw, 4, 1, 220, 262144, 0.95, threads=8)
+    stream = ZipNN(input_format="torch").compress(x.cuda())
+    assert np.array_equal(stream.cpu().numpy(), want)
+    # C ABI directly, DEFAULT workspace, one call
+    L = _native.lib()
+    body = stream[len(plan["header"]):].contiguous()
+    pad = torch.zeros(64 + body.numel() + 16, dtype=torch.uint8, device="cuda")
+    pad[64: 64 + body.numel()] = body
+    out = torch.full((raw.size,), 0xA5, dtype=torch.uint8, device="cuda")
+    ws = torch.empty(_native.decompress_workspace_size(raw.size, 4, 262144), dtype=torch.uint8, device="cuda")
+    rc = L.zipnn_b200_decompress(pad[64:].data_ptr(), body.numel(), 4, 1, 220, 262144, raw.size, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                 torch.cuda.current_stream().cuda_stream, 1)
+    assert rc == 0
+    assert np.array_equal(out.cpu().numpy(), raw)
+
+
+@pytest.mark.gpu
+def test_batch_decompress_matches_single_calls():
+    """zipnn_b200_decompress_batch: tensors of mixed dtype and size (empty, tiny, ragged, multi-coded,
+    one above the sync threshold) in one call == one call per tensor == the original bytes."""
+    rng = np.random.default_rng(9)
+    L = _native.lib()
+    specs = [(torch.bfloat16, 0), (torch.bfloat16, 5), (torch.bfloat16, 300001), (torch.float32, 70001), (torch.float16, 131072 * 3),
+             (torch.float8_e4m3fn, 200000), (torch.bfloat16, 131072 * 40), (torch.float32, 65536 * 3300)]
+    tensors = [torch.from_numpy(rng.standard_normal(n, dtype=np.float32) * np.float32(0.02 if dt != torch.float8_e4m3fn else 0.5)).to(dt)
+               for dt, n in specs]
+    tensors.append(_two_coded_groups_fp32(120))
+    streams, plans = [], []
+    for t in tensors:
+        z = ZipNN(input_format="torch")
+        streams.append(z.compress(t.cuda()))
+        plans.append(z._last_plan)
+    bodies, outs = [], []
+    arr = (_native.BatchItem * len(tensors))()
+    for i, (t, s, p) in enumerate(zip(tensors, streams, plans)):
+        hl = len(p["header"])
+        buf = torch.zeros(64 + s.numel() - hl + 16, dtype=torch.uint8, device="cuda")
+        buf[64: 64 + s.numel() - hl] = s[hl:]
+        bodies.append(buf)
+        n = t.numel() * t.element_size()
+        out = torch.full((max(n, 1),), 0x5A, dtype=torch.uint8, device="cuda")
+        outs.append(out)
+        arr[i].d_body = buf.data_ptr() + 64
+        arr[i].body_len = s.numel() - hl
+        arr[i].num_buf, arr[i].bits_mode, arr[i].bytes_mode = p["num_buf"], p["bit_reorder"], p["byte_reorder"]
+        arr[i].chunk, arr[i].orig = p["chunk"], n
+        arr[i].d_out = out.data_ptr()
+    wsz = C.c_size_t(0)
+    assert L.zipnn_b200_decompress_batch_workspace_size(arr, len(tensors), C.byref(wsz)) == 0
+    ws = torch.empty(wsz.value, dtype=torch.uint8, device="cuda")
+    before = _native.launch_count()
+    rc = L.zipnn_b200_decompress_batch(arr, len(tensors), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream, 1)
+    assert rc == 0
+    launched = _native.launch_count() - before
+    assert launched <= 12, f"{launched} launches for {len(tensors)} tensors: the small ones must share launches"
+    for t, out in zip(tensors, outs):
+        n = t.numel() * t.element_size()
+        assert np.array_equal(out[:n].cpu().numpy(), t.contiguous().view(torch.uint8).numpy())
+    # a corrupt member fails the batch
+    bad = bodies[2].clone()
+    bad[64 + 2] = 9
+    arr[2].d_body = bad.data_ptr() + 64
+    rc = L.zipnn_b200_decompress_batch(arr, len(tensors), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream, 1)
+    assert rc == _native.E_CORRUPT
+    torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+def test_crafted_size_table_cannot_wrap():
+    """A cumulative size near 2^64 in group 0 would wrap the base of group 1 and point its items in front of
+    the body: the whole stream must be rejected, nothing dereferenced."""
+    t = (torch.randn(131072 * 2) * 0.02).to(torch.bfloat16).cuda()    # 2 chunks
+    s = ZipNN(input_format="torch").compress(t).clone()
+    hdr_len, G, K = 32 + 1 + 4, 2, 2
+    cum0_last = hdr_len + G * K + 8 * (0 * K + (K - 1))
+    for evil in ((1 << 64) - 4096, (1 << 64) - 1, 1 << 63, (1 << 40)):
+        bad = s.clone()
+        bad[cum0_last: cum0_last + 8] = torch.frombuffer(bytearray(int(evil).to_bytes(8, "little")), dtype=torch.uint8).cuda()
+        _expect_corrupt(bad)
+        torch.cuda.synchronize()
+    good = ZipNN(input_format="torch").decompress(s)
+    assert torch.equal(good.view(torch.int16), t.view(torch.int16))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sync_max", ["0", "1000000"])
+def test_both_decoder_families_agree(sync_max, monkeypatch):
+    """The per-bitstream CTAs (decode_sync.cuh) and the one-thread-per-bitstream kernels must give the same
+    bytes on the same streams, whatever the size threshold says (ZIPNN_B200_SYNC_MAX forces either)."""
+    monkeypatch.setenv("ZIPNN_B200_SYNC_MAX", sync_max)
+    rng = np.random.default_rng(21)
+    for dt, n in ((torch.bfloat16, 131072 * 9 + 77), (torch.float32, 65536 * 5 + 3), (torch.float16, 131072 * 4), (torch.float8_e4m3fn, 131072 * 3 + 1),
+                  (torch.bfloat16, 2048), (torch.bfloat16, 131072 * 70)):
+        x = torch.from_numpy(rng.standard_normal(n, dtype=np.float32) * np.float32(0.02 if dt != torch.float8_e4m3fn else 0.5)).to(dt)
+        s = ZipNN(input_format="torch").compress(x.cuda())
+        back = ZipNN(input_format="torch").decompress(s)
+        assert torch.equal(back.cpu().view(torch.uint8), x.view(torch.uint8))
+    y = _two_coded_groups_fp32(70)
+    s = ZipNN(input_format="torch").compress(y.cuda())
+    assert torch.equal(ZipNN(input_format="torch").decompress(s).cpu().view(torch.uint8), y.view(torch.uint8))
+    # small chunks (many bitstreams of a few hundred symbols)
+    z = ZipNN(input_format="torch", compression_chunk=4096)
+    x = (torch.randn(50001) * 0.02).to(torch.bfloat16)
+    s = z.compress(x.cuda())
+    assert torch.equal(ZipNN(input_format="torch").decompress(s).cpu().view(torch.uint8), x.view(torch.uint8))

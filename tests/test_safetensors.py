@@ -168,3 +168,25 @@ def test_safetensors_index_matches_the_library(tmp_path):
             t = f.get_tensor(name)
             assert n == t.numel() * t.element_size()
             assert blob[off: off + n] == t.contiguous().view(torch.uint8).numpy().tobytes(), name
+
+
+@pytest.mark.gpu
+def test_tensor_with_many_general_chunks_is_correct_inside_the_with_block(tmp_path):
+    """a tensor with more than 64 chunks that need the general path used to come
+    back unwritten until close().  Read it the way vLLM's iterator does -- copy inside the `with` -- and
+    compare BEFORE close; both the batched and the per-tensor load path."""
+    from zipnn_b200 import SafeOpen, compress_safetensors_file
+    g = torch.Generator().manual_seed(5)
+    big = (torch.randn(65536 * 150, generator=g) * 0.02).to(torch.bfloat16).to(torch.float32)   # two coded groups per chunk
+    small = (torch.randn(4096, generator=g) * 0.02).to(torch.bfloat16)
+    src = str(tmp_path / "m.safetensors")
+    save_file({"big": big, "small": small}, src)
+    path, _, _ = compress_safetensors_file(src)
+    for batch in (True, False):
+        with SafeOpen(path, "pt", "cuda", batch=batch) as f:
+            assert "big" in f.compressed_tensors_metadata
+            got_big = f.get_tensor("big").clone()
+            got_small = f.get_tensor("small").clone()
+            torch.cuda.current_stream().synchronize()
+            assert torch.equal(got_big.cpu(), big), f"batch={batch}"
+            assert torch.equal(got_small.cpu(), small)

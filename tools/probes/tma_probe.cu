@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -109,7 +110,9 @@ static int check_load(EncodeFn enc, uint8_t* d_buf, const std::vector<uint8_t>& 
   return bad_total;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  // one test per process: a faulting kernel poisons the context
+  const int test = argc > 1 ? atoi(argv[1]) : 0;
   EncodeFn enc = get_encode();
   if (!enc) { printf("no cuTensorMapEncodeTiled entry point\n"); return 2; }
   const uint64_t seg = 32768, rows = 256;
@@ -120,49 +123,42 @@ int main() {
   cudaMalloc(&d, total);
   cudaMemcpy(d, h.data(), total, cudaMemcpyHostToDevice);
   int fails = 0;
-  for (int ov = 1; ov >= 0; ov--) {
-    fails += check_load(enc, d, h, 77, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_32B, "load 32B rows, swizzle32", ov) ? 1 : 0;
-    fails += check_load(enc, d, h, 77, seg, rows, 64, CU_TENSOR_MAP_SWIZZLE_64B, "load 64B rows, swizzle64", ov) ? 1 : 0;
-    fails += check_load(enc, d, h, 1029, seg / 2, rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE, "load 16B rows, no swizzle", ov) ? 1 : 0;
+  switch (test) {
+    case 0: fails = check_load(enc, d, h, 0, seg, rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE, "T0 aligned, 16B, no swizzle", false); break;
+    case 1: fails = check_load(enc, d, h, 1029, seg, rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE, "T1 unaligned x, 16B, no swizzle", false); break;
+    case 2: fails = check_load(enc, d, h, 77, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_32B, "T2 unaligned x, 32B, swizzle32", false); break;
+    case 3: fails = check_load(enc, d, h, 77, seg, rows, 64, CU_TENSOR_MAP_SWIZZLE_64B, "T3 unaligned x, 64B, swizzle64", false); break;
+    case 4: fails = check_load(enc, d, h, 1029, seg, rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE, "T4 overlap rows, 16B", true); break;
+    case 5: fails = check_load(enc, d, h, 77, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_32B, "T5 overlap rows, 32B swizzle32", true); break;
+    case 6: fails = check_load(enc, d, h, 77, seg, rows, 64, CU_TENSOR_MAP_SWIZZLE_64B, "T6 overlap rows, 64B swizzle64", true); break;
+    case 7: fails = check_load(enc, d, h, 0, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_NONE, "T7 aligned, 32B, no swizzle", false); break;
+    case 8: {
+      const uint64_t rowb = 65536, nrows = 64;
+      uint8_t* o;
+      cudaMalloc(&o, rowb * nrows);
+      cudaMemset(o, 0, rowb * nrows);
+      CUtensorMap m;
+      cuuint64_t dims[2] = {rowb, nrows};
+      cuuint64_t strides[1] = {rowb};
+      cuuint32_t box[2] = {128, 32}, es[2] = {1, 1};
+      CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, o, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      printf("T8 store map encode -> %d\n", (int)r);
+      if (r == CUDA_SUCCESS) {
+        k_store<<<1, 32>>>(m, 128 * 5, 32);
+        cudaError_t e = cudaDeviceSynchronize();
+        printf("store kernel: %s\n", cudaGetErrorString(e));
+        std::vector<uint8_t> ho(rowb * nrows);
+        cudaMemcpy(ho.data(), o, ho.size(), cudaMemcpyDeviceToHost);
+        int bad = 0;
+        for (int row = 0; row < 32; row++)
+          for (int b = 0; b < 128; b++)
+            if (ho[(size_t)(32 + row) * rowb + 128 * 5 + b] != (uint8_t)(row * 7 + b)) bad++;
+        printf("store: %d mismatching bytes of 4096\n", bad);
+        fails = bad;
+      } else fails = 1;
+    } break;
   }
-  // huge inner dimension (the whole payload as one row) with a row stride of seg
-  {
-    const uint64_t r0 = ((uintptr_t)(d + 77)) & 15;
-    CUtensorMap m;
-    cuuint64_t dims[2] = {total - 4096, rows};
-    cuuint64_t strides[1] = {seg};
-    cuuint32_t box[2] = {32, 32}, es[2] = {1, 1};
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d + 77 - r0, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    printf("whole-payload inner dim, stride seg -> %d\n", (int)r);
-  }
-  // store
-  {
-    const uint64_t rowb = 65536, nrows = 64;
-    uint8_t* o;
-    cudaMalloc(&o, rowb * nrows);
-    cudaMemset(o, 0, rowb * nrows);
-    CUtensorMap m;
-    cuuint64_t dims[2] = {rowb, nrows};
-    cuuint64_t strides[1] = {rowb};
-    cuuint32_t box[2] = {128, 32}, es[2] = {1, 1};
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, o, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    printf("store map encode -> %d\n", (int)r);
-    if (r == CUDA_SUCCESS) {
-      k_store<<<1, 32>>>(m, 128 * 5, 32);
-      cudaError_t e = cudaDeviceSynchronize();
-      printf("store kernel: %s\n", cudaGetErrorString(e));
-      std::vector<uint8_t> ho(rowb * nrows);
-      cudaMemcpy(ho.data(), o, ho.size(), cudaMemcpyDeviceToHost);
-      int bad = 0;
-      for (int row = 0; row < 32; row++)
-        for (int b = 0; b < 128; b++)
-          if (ho[(size_t)(32 + row) * rowb + 128 * 5 + b] != (uint8_t)(row * 7 + b)) bad++;
-      printf("store: %d mismatching bytes of 4096\n", bad);
-      fails += bad ? 1 : 0;
-    } else fails++;
-  }
-  printf("tma_probe: %s\n", fails ? "SOME CHECKS FAILED (see above)" : "all ok");
+  printf("test %d: %s\n", test, fails ? "FAILED" : "ok");
   return 0;
 }

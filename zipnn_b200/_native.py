@@ -23,6 +23,12 @@ _lib = None
 _lock = threading.Lock()
 
 
+class BatchItem(C.Structure):
+    """zipnn_b200_batch_item (include/zipnn_b200.h)."""
+    _fields_ = [("d_body", C.c_void_p), ("body_len", C.c_size_t), ("num_buf", C.c_int), ("bits_mode", C.c_int),
+                ("bytes_mode", C.c_int), ("chunk", C.c_size_t), ("orig", C.c_size_t), ("d_out", C.c_void_p)]
+
+
 class ZipNNNativeError(RuntimeError):
     def __init__(self, status: int, msg: str):
         super().__init__(f"zipnn_b200: {msg} (status {status})")
@@ -50,11 +56,13 @@ def lib() -> C.CDLL:
     global _lib
     with _lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
-                try:
-                    build()
-                except Exception as exc:  # pragma: no cover
+            try:
+                build()   # no-op when the library is newer than every source file
+            except Exception as exc:  # pragma: no cover
+                if not os.path.exists(LIB_PATH):
                     raise ZipNNNativeError(-1, f"libzipnn_b200.so is missing and could not be built: {exc}") from exc
+                import warnings
+                warnings.warn(f"zipnn_b200: libzipnn_b200.so looks older than its sources and could not be rebuilt ({exc}); loading it as is")
             L = C.CDLL(LIB_PATH)
             vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
             szp = C.POINTER(C.c_size_t)
@@ -70,6 +78,8 @@ def lib() -> C.CDLL:
                 "zipnn_b200_decompress_workspace_size_full": (i32, [sz, i32, sz, szp]),
                 "zipnn_b200_compress": (i32, [vp, sz, vp, sz, i32, i32, i32, sz, C.c_float, vp, sz, szp, vp, sz, vp]),
                 "zipnn_b200_decompress": (i32, [vp, sz, i32, i32, i32, sz, sz, vp, vp, sz, vp, i32]),
+                "zipnn_b200_decompress_batch_workspace_size": (i32, [C.POINTER(BatchItem), i32, szp]),
+                "zipnn_b200_decompress_batch": (i32, [C.POINTER(BatchItem), i32, vp, sz, vp, i32]),
                 "zipnn_b200_split": (i32, [vp, sz, i32, i32, vp, sz, vp]),
                 "zipnn_b200_regroup": (i32, [vp, sz, sz, i32, i32, vp, vp]),
                 "zipnn_b200_compress_host": (i32, [vp, sz, vp, sz, i32, i32, i32, sz, C.c_float, vp, sz, szp]),
@@ -90,7 +100,7 @@ EXPORTS = [
     "zipnn_b200_version", "zipnn_b200_strerror", "zipnn_b200_last_cuda_error", "zipnn_b200_sm_count",
     "zipnn_b200_launch_count", "zipnn_b200_compress_bound", "zipnn_b200_compress_workspace_size",
     "zipnn_b200_decompress_workspace_size", "zipnn_b200_decompress_workspace_size_full", "zipnn_b200_compress",
-    "zipnn_b200_decompress",
+    "zipnn_b200_decompress", "zipnn_b200_decompress_batch_workspace_size", "zipnn_b200_decompress_batch",
     "zipnn_b200_split", "zipnn_b200_regroup", "zipnn_b200_compress_host", "zipnn_b200_decompress_host",
     "zipnn_b200_timing_enable", "zipnn_b200_timing_kernel_count", "zipnn_b200_timing_kernel_name",
     "zipnn_b200_timing_collect",

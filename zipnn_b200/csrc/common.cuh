@@ -9,12 +9,13 @@ namespace zb {
 // ---- workspace control block (first 256 bytes of every workspace) ----------------
 struct Ctrl {
   uint32_t error;        // OR of ZIPNN_B200_E_* bits raised by kernels
-  uint32_t pad0;
+  uint32_t overflow_count; // decode: chunks queued for k_decode_overflow (DecodeCfg::olist)
   uint64_t base[4];      // payload offset of group g inside `body`
   uint64_t total_len;    // compress: total stream length
   uint64_t group_total[4];
   uint32_t work_counter; // persistent-kernel work queue
   uint32_t regroup_count; // decode: chunks that go through k_regroup (listed in DecodeCfg::rlist)
+  uint32_t huf_count;     // decode: coded items queued for k_huf_decode_sync (DecodeCfg::hlist)
 };
 static_assert(sizeof(Ctrl) <= 256, "ctrl block");
 constexpr size_t kCtrlBytes = 256;

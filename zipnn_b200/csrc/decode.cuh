@@ -15,15 +15,22 @@
 //   k_regroup            ... and regroup planes (raw / RLE / workspace) into elements; also
 //                        handles chunks with no coded group at all
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
+
+#ifndef ZB_SIDE_SLOTS
+#define ZB_SIDE_SLOTS 2  // 16-byte cp.async slots per lane and side plane of the fused kernel (2 or 4)
+#endif
 
 namespace zb {
 
-enum : uint32_t { kModePlain = 0, kModeFused = 1, kModeGeneral = 2, kModeSkip = 3 };
+enum : uint32_t { kModePlain = 0, kModeFused = 1, kModeGeneral = 2, kModeSkip = 3, kModeOverflow = 4 };
+constexpr uint32_t kOverflowCtas = 32;  // persistent CTAs (each with private plane scratch) for general chunks beyond the slot pool
 constexpr uint32_t kFillBytes = 64;  // replicated RLE byte block per item (read with stride 0)
 
 struct DecodeCfg {
   const uint8_t* body;
+  uint8_t* out;         // decoded tensor (used by the batch kernels; the single-tensor kernels take it as an argument)
   uint64_t body_len;
   int G;
   uint64_t K;
@@ -38,16 +45,44 @@ struct DecodeCfg {
   uint8_t* fill;        // [G*K*kFillBytes]
   uint8_t* planes;      // [slots][G][pstride]
   uint64_t pstride;
-  uint32_t max_slots;
-  uint32_t tail_cap;    // entries in the per-warp tail pool of k_huf_decode_fused (multiple of 8)
+  uint32_t max_slots;   // plane slots of the pool (general chunks 0 .. max_slots-1 by arrival)
+  uint32_t ovf_slots;   // plane slots behind the pool, one per CTA of k_decode_overflow (0: none, an overflow is an error)
+  uint32_t* olist;      // [K] chunks for k_decode_overflow, ctrl->overflow_count of them
+  uint32_t* hlist;      // [G*K] coded items (g*K + c) for k_huf_decode_sync, ctrl->huf_count of them; nullptr: not used
+  uint32_t tma_flags;   // kTmaOut | kTmaSide: which tensor maps of the fused kernel's TmaMaps argument are valid
+  uint64_t k_full;      // chunks of full length (K, or K - 1 with a ragged last chunk)
+  uint64_t side_pred[3];  // payload offset (inside body) of byte plane g's first item IF every group in front of it is all raw
+  uint32_t side_r0[3];    // (body + side_pred[g]) & 15: the tensor maps start at the 16-byte boundary below
 };
+
+
+// A chunk needs plane scratch (several coded groups, a ragged tail, or a table the fused kernel could not hold).
+// The first max_slots of them get a slot in the pool and are decoded by k_huf_decode_planar + k_regroup with
+// the whole GPU; the rest are queued for k_decode_overflow, which works through them with a few persistent
+// CTAs that own their scratch -- slower, but every chunk is written in stream order whatever the stream looks
+// like (an fp32 checkpoint upcast from bf16 has two coded groups in EVERY chunk).
+__device__ __forceinline__ uint32_t assign_general(const DecodeCfg& cfg, uint64_t c) {
+  const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
+  if (s < cfg.max_slots) {
+    cfg.slot[c] = s;
+    cfg.rlist[atomicAdd(&cfg.ctrl->regroup_count, 1u)] = (uint32_t)c;
+    return kModeGeneral;
+  }
+  if (cfg.ovf_slots) {
+    cfg.olist[atomicAdd(&cfg.ctrl->overflow_count, 1u)] = (uint32_t)c;
+    return kModeOverflow;
+  }
+  atomicOr(&cfg.ctrl->error, kErrWorkspace);
+  return kModeSkip;
+}
 
 // ====================================================================================
 // Kernel 1: parse + validate the per-(group,chunk) metadata.
 // Stream body layout (csrc/zipnn_core.c:105-244):
 //   types u8[G][K] | cum u64le[G][K] (inclusive, per group) | group-major payload
 // ====================================================================================
-__global__ void k_decode_meta(DecodeCfg cfg) {
+// Chunks c = first, first + stride, ... of one tensor.
+__device__ __forceinline__ void decode_meta_body(const DecodeCfg& cfg, uint64_t first, uint64_t stride, bool leader) {
   const int G = cfg.G;
   const uint64_t K = cfg.K;
   const uint64_t nitems = (uint64_t)G * K;
@@ -55,17 +90,31 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
   const uint8_t* cum = cfg.body + nitems;
   const uint64_t payload0 = 9 * nitems;
   const uint64_t payload_len = cfg.body_len - payload0;
+  // Group bases: every addition is checked against what is left of the payload, so a crafted size
+  // table cannot wrap a u64 and point an item in front of the body.  With an impossible total
+  // nothing of the stream is trusted: every chunk is skipped.
   uint64_t base[4] = {0, 0, 0, 0};
-  for (int g = 1; g < G; g++) base[g] = base[g - 1] + ld_u64_bytes(cum + 8 * ((uint64_t)(g - 1) * K + (K - 1)));
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int g = 0; g < 4; g++) cfg.ctrl->base[g] = payload0 + base[g];
-    const uint64_t all = base[G - 1] + ld_u64_bytes(cum + 8 * ((uint64_t)(G - 1) * K + (K - 1)));
-    if (all > payload_len) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+  bool totals_ok = true;
+  {
+    uint64_t room = payload_len;
+    for (int g = 0; g < G; g++) {
+      const uint64_t tot = ld_u64_bytes(cum + 8 * ((uint64_t)g * K + (K - 1)));
+      if (tot > room) {
+        totals_ok = false;
+        break;
+      }
+      room -= tot;
+      if (g + 1 < G) base[g + 1] = base[g] + tot;
+    }
   }
-  for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < K; c += (uint64_t)gridDim.x * blockDim.x) {
+  if (leader) {
+    for (int g = 0; g < 4; g++) cfg.ctrl->base[g] = payload0 + base[g];
+    if (!totals_ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+  }
+  for (uint64_t c = first; c < K; c += stride) {
     const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)cfg.chunk) : cfg.chunk;
     int nhuf = 0, last_huf = -1;
-    bool bad_chunk = false;
+    bool bad_chunk = !totals_ok;
     for (int g = 0; g < G; g++) {
       const uint64_t i = (uint64_t)g * K + c;
       const uint64_t hi = ld_u64_bytes(cum + 8 * i);
@@ -76,7 +125,8 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
       d.src_off = payload0 + base[g] + lo;
       d.dec_len = dlen;
       d.pad = 0;
-      bool bad = (hi < lo) || (base[g] + hi > payload_len) || (type > 1) || (hi - lo > 0xFFFFFFFFull);
+      // hi <= this group's total <= payload_len - base[g] (checked above when totals_ok): no sum can wrap
+      bool bad = !totals_ok || (hi < lo) || (hi > payload_len - base[g]) || (type > 1) || (hi - lo > 0xFFFFFFFFull);
       const uint32_t slen = (uint32_t)(hi - lo);
       d.src_len = slen;
       if (type == 0) {
@@ -127,18 +177,55 @@ __global__ void k_decode_meta(DecodeCfg cfg) {
     } else if (nhuf == 1 && last_huf == G - 1 && (chunk_len % 512u) == 0) {
       m = kModeFused;
     } else if (nhuf >= 1) {
-      m = kModeGeneral;
-      const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
-      if (s >= cfg.max_slots) {
-        atomicOr(&cfg.ctrl->error, kErrWorkspace);
-        m = kModeSkip;  // the caller retries with the full workspace
-      } else {
-        cfg.slot[c] = s;
-      }
+      m = assign_general(cfg, c);
     }
     cfg.mode[c] = (uint8_t)m;
-    if (m == kModePlain || m == kModeGeneral) cfg.rlist[atomicAdd(&cfg.ctrl->regroup_count, 1u)] = (uint32_t)c;
+    if (m == kModePlain) cfg.rlist[atomicAdd(&cfg.ctrl->regroup_count, 1u)] = (uint32_t)c;
+    if (cfg.hlist && (m == kModeFused || m == kModeGeneral)) {  // small tensors: one CTA per bitstream (decode_sync.cuh)
+      for (int g = 0; g < G; g++) {
+        const uint64_t i = (uint64_t)g * K + c;
+        if (cfg.items[i].kind == kHuf) cfg.hlist[atomicAdd(&cfg.ctrl->huf_count, 1u)] = (uint32_t)i;
+      }
+    }
   }
+}
+
+__global__ void k_decode_meta(DecodeCfg cfg) {
+  decode_meta_body(cfg, blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x, blockIdx.x == 0 && threadIdx.x == 0);
+}
+
+// ---- batches of tensors (the load path: one launch per kernel for all tensors of a checkpoint shard) ----
+// cfgs[t] describes tensor t (its own workspace slice, body and output); work_start[t] is the exclusive
+// prefix sum of a per-tensor work bound, work_start[n] the total.  A flat work index finds its tensor by
+// binary search, so tensors of any size mix share the grid evenly.
+struct BatchCfg {
+  const DecodeCfg* cfgs;
+  const uint64_t* chunk_start;   // [n + 1] prefix of K
+  const uint64_t* item_start;    // [n + 1] prefix of 4 * G * K (bitstreams)
+  const uint64_t* tile_start;    // [n + 1] prefix of K * tiles_per_chunk (regroup tiles)
+  uint32_t n;
+  uint32_t* error_out;           // OR of every tensor's error word (first word of the batch workspace)
+};
+__device__ __forceinline__ uint32_t batch_find(const uint64_t* start, uint32_t n, uint64_t w) {
+  uint32_t lo = 0, hi = n;  // start[lo] <= w < start[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (start[mid] <= w) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__global__ void k_decode_meta_batch(BatchCfg B) {
+  const uint64_t total = B.chunk_start[B.n];
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t t = batch_find(B.chunk_start, B.n, w);
+    const uint64_t c = w - B.chunk_start[t];
+    decode_meta_body(B.cfgs[t], c, ~0ull >> 1, c == 0);  // exactly one chunk
+  }
+}
+__global__ void k_batch_errors(BatchCfg B) {
+  uint32_t e = 0;
+  for (uint32_t t = threadIdx.x; t < B.n; t += blockDim.x) e |= B.cfgs[t].ctrl->error;
+  if (e) atomicOr(B.error_out, e);
 }
 
 // ====================================================================================
@@ -189,9 +276,9 @@ __device__ __forceinline__ void cp_async_wait() {
 struct BitWindow {
   uint64_t cont;         // bytes [q, q+8) of the stream, little endian
   int32_t s;             // 53 - (bits consumed from the top of `cont`): (uint32_t)(cont >> s) has the next 11 bits in [10:0]
-  uint32_t q;            // byte offset (from gbase) of the container's lowest byte; moves down by 4
+  uint32_t qm;           // q - 8: byte offset (from gbase) of the word the NEXT refill reads; moves down by 4.  The ring
+                         // address of that word is ring_s | (qm & 60): one LOP3, so no second pointer has to be kept
   uint32_t next;         // the word at q - 4
-  uint32_t rd;           // shared-space address of the word at q - 8 (read by the next refill)
   uint32_t ring_s;       // shared-space address of the ring (64-byte aligned)
   uint32_t fetch;        // byte offset (from gbase) of the lowest 16-byte block already requested
   uint32_t start_bit;    // bit offset (from gbase) of the first stream bit (exact-consumption check)
@@ -209,9 +296,9 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
 #pragma unroll 2
   for (int i = 0; i < maxn; i++) {
     const uint32_t f = b.fetch - 16;
-    // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above q
+    // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above q = qm + 8
     // (the container and `next` are in registers; later reads are at q - 8 and below)
-    if (b.fetch >= 16 + b.floor_off && f + kRingBytes >= b.q) {
+    if (b.fetch >= 16 + b.floor_off && f + (kRingBytes - 8) >= b.qm) {
       cp_async16(const_cast<uint8_t*>(b.ring) + (f & (kRingBytes - 1)), b.gbase + f);
       b.fetch = f;
     }
@@ -227,40 +314,52 @@ __device__ __forceinline__ void window_refill(BitWindow& b) {
   if (b.s <= 21) {  // 32 or more bits consumed
     b.cont = (b.cont << 32) | b.next;
     b.s += 32;
-    b.q -= 4u;
-    b.next = lds_u32(b.rd);
-    b.rd = b.ring_s | ((b.rd - 4u) & (kRingBytes - 4u));
+    b.next = lds_u32(b.ring_s | (b.qm & (kRingBytes - 4u)));
+    b.qm -= 4u;
   }
 }
+
+// Frame of reference of a stream at `s`: offsets are taken from a 64-byte aligned address one ring
+// below the stream start, so every offset the decoder forms is non-negative.  `lo` is the first
+// readable byte of the buffer.  Returns the stream's byte offset in that frame.
+__device__ __forceinline__ uint32_t window_frame(BitWindow& b, const uint8_t* s, const uint8_t* lo, uint8_t* ring) {
+  b.ring = ring;
+  b.ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  b.gbase = reinterpret_cast<const uint8_t*>(((uintptr_t)s & ~(uintptr_t)(kRingBytes - 1)) - kRingBytes);
+  b.floor_off = (b.gbase < lo) ? (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15) : 0u;
+  const uint32_t s_off = (uint32_t)((uintptr_t)s - (uintptr_t)b.gbase);
+  b.start_bit = 8u * s_off;
+  return s_off;
+}
+// Position the window so that the next unread bit is the one below bit offset `mark` (> start_bit).
+__device__ __forceinline__ void window_seek(BitWindow& b, uint32_t mark) {
+  const uint32_t top_byte = (mark - 1) >> 3;
+  const uint32_t q = (top_byte & ~3u) - 4u;
+  b.qm = q - 8u;
+  b.s = 53 - (int32_t)(8u * (q + 8u) - mark);  // 1..32 bits lie above the first unread bit
+  b.fetch = (top_byte & ~15u) + 16;
+  ring_top_up(b, (int)(kRingBytes / 16));
+  cp_async_commit();
+  cp_async_wait<0>();
+  b.cont = ((uint64_t)ring_word(b.ring, q + 4u) << 32) | ring_word(b.ring, q);
+  b.next = ring_word(b.ring, q - 4u);
+}
+// Bit offset of the lowest consumed bit (== start_bit when the stream has been consumed exactly).
+__device__ __forceinline__ uint32_t window_tell(const BitWindow& b) { return 8u * (b.qm + 16u) - (uint32_t)(53 - b.s); }
 
 // s points at the stream (len bytes); `lo` is the first readable byte of the buffer.
 __device__ __forceinline__ bool window_init(BitWindow& b, const uint8_t* s, uint32_t len, const uint8_t* lo, uint8_t* ring) {
   const uint8_t lastb = s[len - 1];
   if (lastb == 0) return false;
-  b.ring = ring;
-  b.gbase = reinterpret_cast<const uint8_t*>(((uintptr_t)s & ~(uintptr_t)(kRingBytes - 1)) - kRingBytes);
-  // (one ring below the stream start keeps every offset the decoder forms non-negative)
-  b.floor_off = (b.gbase < lo) ? (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15) : 0u;
-  const uint32_t s_off = (uint32_t)((uintptr_t)s - (uintptr_t)b.gbase);
+  const uint32_t s_off = window_frame(b, s, lo, ring);
   const uint32_t mark = 8u * (s_off + len - 1) + (uint32_t)hb32(lastb);  // bit offset of the end mark
-  b.start_bit = 8u * s_off;
   if (mark == b.start_bit) return false;
-  const uint32_t top_byte = (mark - 1) >> 3;
-  b.q = (top_byte & ~3u) - 4u;
-  b.s = 53 - (int32_t)(8u * (b.q + 8u) - mark);  // 1..32 bits lie above the first unread bit
-  b.fetch = (top_byte & ~15u) + 16;
-  ring_top_up(b, (int)(kRingBytes / 16));
-  cp_async_commit();
-  cp_async_wait<0>();
-  b.cont = ((uint64_t)ring_word(ring, b.q + 4u) << 32) | ring_word(ring, b.q);
-  b.next = ring_word(ring, b.q - 4u);
-  b.ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-  b.rd = b.ring_s | ((b.q - 8u) & (kRingBytes - 4u));
+  window_seek(b, mark);
   return true;
 }
 
 __device__ __forceinline__ bool window_exact(const BitWindow& b) {
-  return 8u * (b.q + 8u) - (uint32_t)(53 - b.s) == b.start_bit;  // every bit down to the stream start consumed, none below
+  return window_tell(b) == b.start_bit;  // every bit down to the stream start consumed, none below
 }
 
 // ---- decode tables ------------------------------------------------------------------
@@ -553,6 +652,35 @@ __device__ __forceinline__ bool setup_item(DecodeSmem& S, const uint8_t* body, c
 // ====================================================================================
 // Kernel 2a: general mode -- decode coded planes into workspace planes.
 // ====================================================================================
+// One lane = one bitstream of item `d` (all 32 lanes call; 4 lanes per item slot): decode it into the
+// item's workspace plane.
+__device__ __forceinline__ void planar_decode_item(DecodeSmem& S, const DecodeCfg& cfg, const ItemDesc& d, bool active, int slot, int stream,
+                                                   uint8_t* plane) {
+  const int lane = threadIdx.x & 31;
+  StreamSetup st;
+  if (!setup_item(S, cfg.body, d, active, slot, stream, cfg.ctrl, st)) return;
+  uint8_t* dst = plane + st.out_off;
+  BitWindow b;
+  const LutFull lut{S.lut[slot], st.lg};
+  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
+  if (ok) {
+    uint32_t done = 0;
+    if ((((uintptr_t)dst) & 15) == 0) {
+      const uint32_t n16 = st.count >> 4;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+      for (uint32_t it = 0; it < n16; it++) {
+        uint32_t o[4];
+        decode16(b, lut, o);
+        d4[it] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      done = n16 << 4;
+    }
+    for (; done < st.count; done++) dst[done] = (uint8_t)decode1(b, lut);
+    ok = window_exact(b);
+  }
+  if (!ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+}
+
 __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
@@ -575,70 +703,151 @@ __global__ void __launch_bounds__(32) k_huf_decode_planar(DecodeCfg cfg) {
     }
   }
   if (__ballot_sync(0xffffffffu, active) == 0) return;
-  StreamSetup st;
-  if (!setup_item(S, cfg.body, d, active, slot, stream, cfg.ctrl, st)) return;
-  uint8_t* dst = cfg.planes + ((uint64_t)cfg.slot[c] * cfg.G + g) * cfg.pstride + st.out_off;
-  BitWindow b;
-  const LutFull lut{S.lut[slot], st.lg};
-  bool ok = window_init(b, st.p + st.s_off, st.s_len, cfg.body, S.ring[lane]);
-  if (ok) {
-    uint32_t done = 0;
-    if ((((uintptr_t)dst) & 15) == 0) {
-      const uint32_t n16 = st.count >> 4;
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
-      for (uint32_t it = 0; it < n16; it++) {
-        uint32_t o[4];
-        decode16(b, lut, o);
-        d4[it] = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-      done = n16 << 4;
-    }
-    for (; done < st.count; done++) dst[done] = (uint8_t)decode1(b, lut);
-    ok = window_exact(b);
-  }
-  if (!ok) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+  planar_decode_item(S, cfg, d, active, slot, stream, active ? cfg.planes + ((uint64_t)cfg.slot[c] * cfg.G + g) * cfg.pstride : nullptr);
 }
 
 // ====================================================================================
-// Kernel 2b: fused mode.  The lane that decodes 16 symbols of the coded plane also fetches
+// Kernel 2b: fused mode.  The lane that decodes 16 symbols of the coded plane also takes
 // the 16 matching bytes of each other plane (raw bytes in the stream at any alignment, or
-// a replicated RLE block read with stride 0), interleaves, un-rotates and stores 16*G bytes
-// of elements.  The other planes are loaded as aligned 16-byte blocks one iteration ahead.
-// Shared memory per warp: 8 x (256-entry primary + 256-entry tail) + 32 rings = 12 KiB.
+// a replicated RLE block read with stride 0), interleaves, un-rotates and emits 16*G bytes
+// of elements.
+//
+// Persistent: the grid is (SM count x resident warps per SM) one-warp CTAs and CTA i takes
+// the chunk groups i, i + grid, ...  A bitstream is serial, so a group costs the same ~2 ms
+// however the launch is shaped; with one CTA per group the last, partial wave lands on a
+// few SMs that run it at full-wave speed while the rest idle.  A static round-robin leaves
+// every SM the same share of the remainder.
+//
+// Bulk tensor copies (TMA) carry everything that is regular:
+//   * side planes: for full chunks whose other planes are all stored raw (what float
+//     tensors produce) the 32 quarter-plane segments of a warp lie at a fixed stride in
+//     the stream -- byte plane g of chunk c at side_pred[g] + c * plane_len, stream j a
+//     quarter plane further.  A 2-D tensor map over the payload (inner = bytes of one
+//     segment, outer = segment index) delivers the next 16*T bytes of all 32 lanes as one
+//     [32][16*T] box, at ANY byte alignment, into a swizzled tile that the lanes read with
+//     conflict-free LDS.128 -- no per-lane cp.async (32 LSU wavefronts per instruction,
+//     26 % of all shared-memory wavefronts of the round-1 kernel), no funnel shifts.
+//   * output: the [32][128] stage is written with one 2-D bulk store per row (the 32 rows
+//     are a quarter chunk apart), SWIZZLE_128B = the XOR pattern the stage already used.
+// Anything irregular (RLE side planes, the ragged last chunk, groups with idle lanes, a
+// driver without the tensor-map entry point) takes the cp.async / LDS+STG path below, in
+// the same kernel.
 // ====================================================================================
-// Shared memory of one warp (dynamic, tail_cap is a launch parameter):
-//   prim  [8][256] u16   4 KiB   shared primary tables (PB = 0), or 3 KiB holding [32][32] u16 private columns (PB = 5)
-//   tail  [tail_cap] u16         tail tables of the 8 chunks packed back to back (bf16 / fp32
-//                                exponent planes need ~16 entries each, fp16 ~90, fp8 ~150)
-//   ring  [32][64]       2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
-//   stage [32][128]      4 KiB   one 128-byte output row per lane, 16-byte units XOR-swizzled;
-//                                the tANS scratch of the parse aliases it (512 B per chunk)
-//   side  [G-1][32][64]  2 KiB per side plane: blocks of the other planes in flight (cp.async)
-// bf16: 3 KiB table area (2 KiB of private 5-bit u16 columns) + tail_cap 1024 + one side plane = 13 KiB
-// -> 16 warps per SM.
-struct FusedSmem {
-  uint16_t (*prim)[256];
-  uint16_t* tail;
-  uint8_t (*ring)[kRingBytes];
-  uint8_t (*stage)[128];
-  uint8_t* side;   // [G-1][32][64]: four 16-byte slots per lane and side plane for the blocks in flight
+struct alignas(64) TmaMaps {
+  CUtensorMap out;      // bytes {chunk / 4, 4 * k_full}, box {128, 32}, SWIZZLE_128B
+  CUtensorMap side[3];  // per side plane: bytes {plane_len / 4 (+16), 4 * k_full}, box {16 * T, 32}
 };
-// PB = 0: shared 256-entry u16 primaries (4 KiB).  PB = 5: private u16 columns, 2 KiB, which must start
-// on a 2 KiB boundary of the shared address space (LutCol); the dynamic buffer is 1 KiB aligned, so the
-// area is 3 KiB and the columns start 0 or 1 KiB into it.
-__host__ __device__ constexpr size_t fused_prim_bytes(int pb) { return pb == 0 ? (size_t)kDecItemsPerWarp * 512 : (size_t)3072; }
-__host__ __device__ inline size_t fused_smem_bytes(uint32_t tail_cap, int pb, int G) {
-  return fused_prim_bytes(pb) + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128 + (size_t)(G - 1) * 32 * 64;
+enum : uint32_t { kTmaOut = 1u, kTmaSide = 2u };
+
+__device__ __forceinline__ void mbar_init(uint32_t bar_s, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
 }
-__device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw, uint32_t tail_cap, int pb) {
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(bar_s), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_s, const CUtensorMap* map, uint32_t x, uint32_t y, uint32_t bar_s) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_s),
+               "l"((uint64_t)(uintptr_t)map), "r"(x), "r"(y), "r"(bar_s)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_s, uint32_t x, uint32_t y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)(uintptr_t)map), "r"(src_s), "r"(x), "r"(y)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Shared memory of one warp (dynamic; offsets from the 1 KiB aligned base, A = its shared address):
+//   PB = 5 (bf16 / fp32 exponent planes):
+//     cols  [32][32] u16   2 KiB   private 5-bit columns; must start on a 2 KiB boundary of the shared
+//                                  address space (LutCol): at A's next 2 KiB boundary, 0 or 1 KiB in
+//     gap                  1 KiB   the other KiB of the first three: side tiles / slots go here
+//   PB = 0 (fp16 / fp8): prim [8][256] u16, 4 KiB
+//   tail  [tail_cap] u16           tail tables of the 8 chunks packed back to back; the last 16 bytes
+//                                  of its 2 (4) KiB hold the two mbarriers
+//   ring  [32][64]         2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
+//   stage [32][128]        4 KiB   one 128-byte output row per lane (1 KiB aligned, 16-byte units XOR-
+//                                  swizzled by the row); the tANS scratch of the parse aliases it
+//   side                           TMA: 2 stages x (G-1) tiles of [32][16*T]; cp.async path: (G-1) x 1 KiB
+//                                  of slots (2 per lane).  The two uses alias.
+// bf16: 2 + 1 + 2 + 2 + 4 + 1 = 12 KiB -> 17 warps per SM;  fp32: 13 KiB -> 16.
+template <int G>
+struct FusedGeom {
+  static constexpr int kIters = 8 / G;                 // iterations (16 symbols) per 128-byte output row
+  static constexpr int kTileIters = (G == 2) ? 2 : 1;  // iterations covered by one side tile
+  static constexpr int kTilesPerRow = kIters / kTileIters;
+  static constexpr uint32_t kTileBytes = 32u * 16u * kTileIters;  // one plane, one stage
+  static constexpr int NS = (G > 1) ? G - 1 : 1;
+  static constexpr uint32_t kSlotBytes = 512u * ZB_SIDE_SLOTS;                       // one side plane's cp.async slots (32 lanes)
+  static constexpr uint32_t kSideExtra = (G == 1) ? 0u : (uint32_t)(G - 1) * kSlotBytes - (ZB_SIDE_SLOTS == 2 ? 1024u : 0u);  // PB = 5: beyond the 1 KiB gap
+  static constexpr uint32_t kSideAll = (G == 1) ? 0u : (uint32_t)(G - 1) * kSlotBytes;    // PB = 0: everything
+};
+__host__ __device__ constexpr uint32_t fused_tail_bytes(int pb) { return pb == 0 ? 4096u : 2048u; }
+__host__ __device__ constexpr uint32_t fused_tail_cap(int pb) { return (fused_tail_bytes(pb) - 16u) / 2u; }  // entries (multiple of 8)
+template <int G>
+__host__ __device__ constexpr size_t fused_smem_bytes(int pb) {
+  return (pb == 0 ? (size_t)4096 + FusedGeom<G>::kSideAll : (size_t)3072 + FusedGeom<G>::kSideExtra) + fused_tail_bytes(pb) + 32 * kRingBytes + 32 * 128;
+}
+struct FusedSmem {
+  unsigned char* raw;
+  uint32_t base_s;     // shared address of raw
+  uint32_t table_off;  // cols (PB = 5) or prim (PB = 0)
+  uint32_t gap_off;    // PB = 5: the free KiB next to the columns
+  uint32_t tail_off, bar_off, ring_off, stage_off, side_off;
+  __device__ __forceinline__ uint16_t* tail() const { return reinterpret_cast<uint16_t*>(raw + tail_off); }
+  __device__ __forceinline__ uint8_t (*ring() const)[kRingBytes] { return reinterpret_cast<uint8_t (*)[kRingBytes]>(raw + ring_off); }
+  __device__ __forceinline__ uint8_t (*stage() const)[128] { return reinterpret_cast<uint8_t (*)[128]>(raw + stage_off); }
+};
+template <int G, int PB>
+__device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw) {
   FusedSmem S;
-  const size_t pbytes = fused_prim_bytes(pb);
-  S.prim = reinterpret_cast<uint16_t (*)[256]>(raw);
-  S.tail = reinterpret_cast<uint16_t*>(raw + pbytes);
-  S.ring = reinterpret_cast<uint8_t (*)[kRingBytes]>(raw + pbytes + (size_t)tail_cap * 2);
-  S.stage = reinterpret_cast<uint8_t (*)[128]>(raw + pbytes + (size_t)tail_cap * 2 + 32 * kRingBytes);
-  S.side = raw + pbytes + (size_t)tail_cap * 2 + 32 * kRingBytes + 32 * 128;
+  S.raw = raw;
+  S.base_s = (uint32_t)__cvta_generic_to_shared(raw);
+  // Opaque from here on: ptxas otherwise treats every address derived from it as "window base + constant"
+  // and REBUILDS the base (S2R SR_CgaCtaId, MOV, LEA) at each use -- three extra instructions per symbol
+  // in front of the predicated tail lookup (measured: +13 % instructions, 8.7 -> 10.4 ms).
+  asm volatile("" : "+r"(S.base_s));
+  uint32_t at;
+  if (PB == 0) {
+    S.table_off = 0;
+    S.gap_off = 0;
+    at = 4096;
+  } else {
+    S.table_off = (2048u - (S.base_s & 2047u)) & 2047u;  // 0 or 1024 for a 1 KiB aligned base
+    S.gap_off = S.table_off ? 0u : 2048u;
+    at = 3072;
+  }
+  S.tail_off = at;
+  S.bar_off = at + fused_tail_bytes(PB) - 16u;
+  at += fused_tail_bytes(PB);
+  S.ring_off = at;
+  at += 32 * kRingBytes;
+  S.stage_off = at;  // 1 KiB multiple in both layouts
+  at += 32 * 128;
+  S.side_off = at;
   return S;
+}
+// Shared address of side tile (stage st, plane g) / of plane g's cp.async slots.
+template <int G, int PB>
+__device__ __forceinline__ uint32_t side_tile_s(const FusedSmem& S, int st, int g) {
+  using Geo = FusedGeom<G>;
+  const uint32_t idx = (uint32_t)(st * (G - 1) + g);
+  if (PB == 0) return S.base_s + S.side_off + idx * Geo::kTileBytes;
+  constexpr uint32_t in_gap = 1024u / Geo::kTileBytes;
+  return idx < in_gap ? S.base_s + S.gap_off + idx * Geo::kTileBytes : S.base_s + S.side_off + (idx - in_gap) * Geo::kTileBytes;
+}
+template <int G, int PB>
+__device__ __forceinline__ uint32_t side_slots_s(const FusedSmem& S, int g) {
+  constexpr uint32_t sb = FusedGeom<G>::kSlotBytes;
+  if (PB == 0 || ZB_SIDE_SLOTS != 2) return S.base_s + S.side_off + (uint32_t)g * sb;
+  return g == 0 ? S.base_s + S.gap_off : S.base_s + S.side_off + (uint32_t)(g - 1) * sb;   // two slots: plane 0 fits the 1 KiB gap
 }
 static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in 4 stage rows");
 
@@ -647,8 +856,8 @@ struct SidePlane {
   uint32_t shift;    // byte offset (0..15) of that byte inside the block
   uint32_t step;     // 1 for stream bytes, 0 for an RLE fill block
   uint4 a, b;        // blocks k, k+1
-  uint32_t slots_s;  // shared address of this lane's four 16-byte slots; block j waits in
-  uint32_t swz;      // slot (j & 3) ^ swz -- the XOR spreads the lanes of a quarter warp over all banks
+  uint32_t slots_s;  // shared address of this lane's two 16-byte slots; block j waits in slot (j & 1) ^ swz
+  uint32_t swz;      // -- the XOR spreads the 8 lanes of a quarter warp over all banks
 };
 
 // The blocks in flight (k+2, k+3) are NOT held in registers.  A register load has a first use, and ptxas
@@ -657,8 +866,7 @@ struct SidePlane {
 // iteration that requested it -- 12 % of all stall samples sat on that one instruction, and an L2
 // prefetch only shortened the wait.  cp.async has no destination register: block k+3 is requested
 // at the top of iteration k, joins the commit groups of the stream ring, and an LDS picks it up at
-// the end of iteration k+1.  64 bytes of shared memory per lane and plane.  Measured: bf16 10.43 ->
-// 9.69 ms (16 GiB), fp32 1285 -> 1456 GB/s (4 GiB).
+// the end of iteration k+1, after which its slot is free for block k+5: two slots per lane and plane.
 __device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem_src) : "memory");
 }
@@ -667,7 +875,8 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
 }
-__device__ __forceinline__ uint32_t side_slot(const SidePlane& sp, uint32_t j) { return sp.slots_s + (((j & 3u) ^ sp.swz) << 4); }
+constexpr uint32_t kSideSlots = ZB_SIDE_SLOTS;  // 16-byte slots per lane and side plane (2 or 4)
+__device__ __forceinline__ uint32_t side_slot(const SidePlane& sp, uint32_t j) { return sp.slots_s + (((j & (kSideSlots - 1u)) ^ sp.swz) << 4); }
 
 __device__ __forceinline__ uint4 ldg128(const uint4* p) { return __ldg(p); }
 // 16 bytes starting `shift` bytes into the 32-byte pair (a, b).
@@ -694,41 +903,24 @@ __device__ __forceinline__ void unrotate_planes(uint32_t& lo, uint32_t& hi) {
   lo = ((e << 7) & 0x80808080u) | (sm & 0x7F7F7F7Fu);
 }
 
-// One iteration: 16 symbols of the coded (top) plane + the matching bytes of the G-1 other
-// planes -> 16*G bytes of elements.  guard = clamp the look-ahead block loads to the end of
-// the stream buffer (only the last iterations of a stream can reach past it).
 // Output rows.  A lane produces 16*G bytes per iteration, 64 KiB away from its neighbours'
 // data, so direct stores cost one LSU wavefront per lane.  Instead each lane fills a 128-byte
-// row in shared memory (16-byte units XOR-swizzled by the lane so that the 128-bit stores of 8
-// lanes cover 32 banks), and every 8/G iterations the warp writes the 32 rows out with 8 stores
-// that each cover four whole 128-byte lines.
+// row in shared memory (16-byte units XOR-swizzled by the row so that the 128-bit stores of 8
+// lanes cover 32 banks -- which is exactly the tensor-map SWIZZLE_128B pattern), and once per row
+// the 32 rows leave with one bulk tensor store (or, on the fallback path, 8 stores of four whole
+// 128-byte lines each).
 __device__ __forceinline__ uint4* stage_unit(uint8_t (*stage)[128], int row, int unit) {
   return reinterpret_cast<uint4*>(&stage[row][((unit ^ row) & 7) * 16]);
 }
 
-// One iteration: 16 symbols of the coded (top) plane + the matching bytes of the G-1 other
-// planes -> 16*G bytes of elements into units [unit0, unit0+G) of the lane's stage row.
-// guard = clamp the look-ahead block loads to the end of the stream buffer (only the last
-// iterations of a stream can reach past it).
-template <int G, class LUT>
-__device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
-                                                const uint4* hi_block, bool guard, bool rot, uint8_t (*stage)[128], int lane, int unit0, uint32_t it) {
-  if (G > 1) {
-#pragma unroll
-    for (int g = 0; g < G - 1; g++) {  // block k+3 of every side plane, used two iterations later
-      const uint4* nb = side[g].blk + 3 * side[g].step;
-      if (guard && side[g].step && nb > hi_block) nb = hi_block;  // (an RLE fill block lives in the workspace)
-      cp_async16_s(side_slot(side[g], it + 3u), nb);  // joins the next commit group of decode16
-    }
-  }
-  uint32_t pl[G][4];
-  decode16(b, lut, pl[G - 1]);
+// Planes of 16 elements (pl[g][q] = bytes 4q..4q+3 of plane g) -> un-rotated, interleaved, into
+// units [unit0, unit0 + G) of the lane's stage row.
+template <int G>
+__device__ __forceinline__ void emit_elements(uint32_t (&pl)[G][4], bool rot, uint8_t (*stage)[128], int lane, int unit0) {
   if (G == 1) {
     *stage_unit(stage, lane, unit0) = make_uint4(pl[0][0], pl[0][1], pl[0][2], pl[0][3]);
     return;
   }
-#pragma unroll
-  for (int g = 0; g < G - 1; g++) take16(side[g].a, side[g].b, side[g].shift, pl[g]);
   if (rot) {
 #pragma unroll
     for (int q = 0; q < 4; q++) unrotate_planes(pl[(G - 2) % G][q], pl[G - 1][q]);
@@ -753,205 +945,284 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, Si
   }
 #pragma unroll
   for (int q = 0; q < G; q++) *stage_unit(stage, lane, unit0 + q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+// One iteration of the cp.async path: 16 symbols of the coded (top) plane + the matching bytes of
+// the G-1 other planes -> 16*G bytes of elements into units [unit0, unit0+G) of the lane's stage row.
+// guard = clamp the look-ahead block loads to the end of the stream buffer (only the last
+// iterations of a stream can reach past it).  wait_store: the previous row's bulk store still
+// reads the stage -- lane 0 waits for it after the decode, right before the first write.
+template <int G, class LUT>
+__device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, SidePlane (&side)[(G > 1) ? G - 1 : 1],
+                                                const uint4* hi_block, bool guard, bool rot, uint8_t (*stage)[128], int lane, int unit0, uint32_t it,
+                                                bool wait_store) {
+  if (G > 1) {
 #pragma unroll
-  for (int g = 0; g < G - 1; g++) {
-    side[g].a = side[g].b;
-    side[g].b = lds_u128(side_slot(side[g], it + 2u));  // requested in the previous iteration, landed since
-    side[g].blk += side[g].step;
+    for (int g = 0; g < G - 1; g++) {  // block k+3 of every side plane, used two iterations later
+      const uint4* nb = side[g].blk + 3 * side[g].step;
+      if (guard && side[g].step && nb > hi_block) nb = hi_block;  // (an RLE fill block lives in the workspace)
+      cp_async16_s(side_slot(side[g], it + 3u), nb);  // joins the next commit group of decode16
+    }
+  }
+  uint32_t pl[G][4];
+  decode16(b, lut, pl[G - 1]);
+  if (wait_store) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
+  if (G > 1) {
+#pragma unroll
+    for (int g = 0; g < G - 1; g++) take16(side[g].a, side[g].b, side[g].shift, pl[g]);
+  }
+  emit_elements<G>(pl, rot, stage, lane, unit0);
+  if (G > 1) {
+#pragma unroll
+    for (int g = 0; g < G - 1; g++) {
+      side[g].a = side[g].b;
+      side[g].b = lds_u128(side_slot(side[g], it + 2u));  // requested in the previous iteration, landed since
+      side[g].blk += side[g].step;
+    }
   }
 }
 
 template <int G, int PB>
-__global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t* __restrict__ out, const __grid_constant__ TmaMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const FusedSmem S = fused_smem_carve(smem_raw, cfg.tail_cap, PB);
+  using Geo = FusedGeom<G>;
   using LUT = typename std::conditional<PB == 0, LutTwo, LutCol<(PB ? PB : 5)>>::type;
-  // private columns: first 2 KiB boundary of the shared address space inside the 3 KiB table area
-  const uint32_t col_off = PB ? ((2048u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 2047u)) & 2047u) : 0u;
+  constexpr int kIters = Geo::kIters;
+  constexpr int NS = Geo::NS;
+  const FusedSmem S = fused_smem_carve<G, PB>(smem_raw);
   const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
   const uint64_t K = cfg.K;
-  const uint64_t c = (uint64_t)blockIdx.x * kDecItemsPerWarp + slot;
-  const bool active = (c < K) && cfg.mode[c] == kModeFused;
-  if (__ballot_sync(0xffffffffu, active) == 0) return;
-  if (PB != 0 && col_off > 1024u) {  // the dynamic buffer is not 1 KiB aligned: cannot happen, but never decode wrongly
-    if (lane == 0) atomicOr(&cfg.ctrl->error, kErrUnsupported);
+  const uint64_t ngroups = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
+  if (PB != 0 && S.table_off > 1024u) {  // the dynamic buffer is not 1 KiB aligned: cannot happen, but never decode wrongly
+    if (lane == 0 && blockIdx.x == 0) atomicOr(&cfg.ctrl->error, kErrUnsupported);
     return;
   }
+  bool store_pending = false;   // a bulk store of this warp may still be reading the stage
+  uint8_t (*const stage)[128] = S.stage();
+  const uint32_t stage_s = S.base_s + S.stage_off;
+  const bool rot = (cfg.bits_mode == 1) && (G > 1);
+  const uint4* hi_block = reinterpret_cast<const uint4*>(((uintptr_t)(cfg.body + cfg.body_len) - 1) & ~(uintptr_t)15);
 
-  ItemDesc d;  // the coded plane: always group G-1 in fused mode
-  d.kind = kRaw;
-  d.src_off = 0;
-  d.src_len = d.dec_len = 0;
-  if (active) d = cfg.items[(uint64_t)(G - 1) * K + c];
-
-  // ---- table description -> two-level table (lane 0 of each chunk) ----
-  int lg = 0, hsize = -1, x_long = 0;
-  uint32_t tail_at = 0;
-  {
-    uint8_t* weights = &S.ring[0][0] + slot * 256;
-    const bool builder = active && stream == 0;
-    int nsym = 0;
-    if (builder) {
-      FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&S.stage[4 * slot][0]);
-      hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
-      if (hsize >= 0) {
-        x_long = PB == 0 ? lut2_tail_size(weights, nsym, lg) : lut_tail_size(weights, nsym, lg, PB);
-        if (x_long < 0) hsize = -1;
-      }
-    }
-    // the 8 tails share one pool: exclusive prefix over the chunks of the warp
-    {
-      const uint32_t mine = (builder && hsize >= 0) ? (uint32_t)x_long : 0u;
-      uint32_t run = mine;
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, run, o);
-        if (lane >= o) run += v;
-      }
-      tail_at = run - mine;
-      if (builder && hsize >= 0 && run > cfg.tail_cap) hsize = -1;  // does not fit: general path
-    }
-    if (builder) {
-      if (hsize >= 0) {
-        if (PB == 0) fill_lut2(S.prim[slot], S.tail + tail_at, weights, nsym, lg);
-      } else {
-        // Not an error yet: a table that needs the big scratch, a long tail or log 12, or a
-        // corrupt one.  Hand the chunk to the general kernels, which decide.
-        const uint32_t s = atomicAdd(&cfg.ctrl->work_counter, 1u);
-        if (s >= cfg.max_slots) {
-          atomicOr(&cfg.ctrl->error, kErrWorkspace);
-          cfg.mode[c] = (uint8_t)kModeSkip;
-        } else {
-          cfg.slot[c] = s;
-          cfg.mode[c] = (uint8_t)kModeGeneral;
-          cfg.rlist[atomicAdd(&cfg.ctrl->regroup_count, 1u)] = (uint32_t)c;
-        }
-      }
+  for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const uint64_t c = grp * kDecItemsPerWarp + slot;
+    const bool active = (c < K) && cfg.mode[c] == kModeFused;
+    if (__ballot_sync(0xffffffffu, active) == 0) continue;
+    if (store_pending) {  // the parse scratch aliases the stage
+      if (lane == 0) tma_store_wait_read();
+      store_pending = false;
     }
     __syncwarp();
-    lg = __shfl_sync(0xffffffffu, lg, lane & ~3);
-    hsize = __shfl_sync(0xffffffffu, hsize, lane & ~3);
-    x_long = __shfl_sync(0xffffffffu, x_long, lane & ~3);
-    tail_at = __shfl_sync(0xffffffffu, tail_at, lane & ~3);
-    if (PB != 0) {  // private columns: the 4 lanes of a chunk fill their own copy in parallel
-      nsym = __shfl_sync(0xffffffffu, nsym, lane & ~3);
-      if (active && hsize >= 0)
-        fill_lut_col<(PB ? PB : 5)>(reinterpret_cast<uint16_t*>(smem_raw + col_off) + lane, S.tail + tail_at, stream == 0, weights, nsym, lg);
-    }
-    __syncwarp();  // the ring and the stage (aliased by the parse scratch) are free from here on
-  }
-  // From here on no lane leaves early: the output flush is a warp-wide exchange.
-  bool live = active && hsize >= 0;
 
-  // ---- jump table (huf_decompress.c:283-290) ----
-  const uint8_t* p = cfg.body + d.src_off + (live ? hsize : 0);
-  const uint32_t rest = live ? d.src_len - (uint32_t)hsize : 0;
-  uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
-  if (live) {
-    bool ok = rest >= 10;
-    if (ok) {
-      l0 = p[0] | (p[1] << 8);
-      l1 = p[2] | (p[3] << 8);
-      l2 = p[4] | (p[5] << 8);
-      ok = l0 + l1 + l2 + 6 <= rest;
-      l3 = rest - (l0 + l1 + l2 + 6);
-      ok = ok && l0 && l1 && l2 && l3;
+    ItemDesc d;  // the coded plane: always group G-1 in fused mode
+    d.kind = kRaw;
+    d.src_off = 0;
+    d.src_len = d.dec_len = 0;
+    if (active) d = cfg.items[(uint64_t)(G - 1) * K + c];
+
+    // ---- table description -> two-level table (lane 0 of each chunk) ----
+    int lg = 0, hsize = -1, x_long = 0;
+    uint32_t tail_at = 0;
+    {
+      uint8_t* weights = &S.ring()[0][0] + slot * 256;
+      const bool builder = active && stream == 0;
+      int nsym = 0;
+      if (builder) {
+        FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&stage[4 * slot][0]);
+        hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
+        if (hsize >= 0) {
+          x_long = PB == 0 ? lut2_tail_size(weights, nsym, lg) : lut_tail_size(weights, nsym, lg, PB);
+          if (x_long < 0) hsize = -1;
+        }
+      }
+      // the 8 tails share one pool: exclusive prefix over the chunks of the warp
+      {
+        const uint32_t mine = (builder && hsize >= 0) ? (uint32_t)x_long : 0u;
+        uint32_t run = mine;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, run, o);
+          if (lane >= o) run += v;
+        }
+        tail_at = run - mine;
+        if (builder && hsize >= 0 && run > fused_tail_cap(PB)) hsize = -1;  // does not fit: general path
+      }
+      if (builder) {
+        if (hsize >= 0) {
+          if (PB == 0) fill_lut2(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + 256 * slot, S.tail() + tail_at, weights, nsym, lg);
+        } else {
+          // Not an error yet: a table that needs the big scratch, a long tail or log 12, or a
+          // corrupt one.  Hand the chunk to the general kernels, which decide.
+          cfg.mode[c] = (uint8_t)assign_general(cfg, c);
+        }
+      }
+      __syncwarp();
+      lg = __shfl_sync(0xffffffffu, lg, lane & ~3);
+      hsize = __shfl_sync(0xffffffffu, hsize, lane & ~3);
+      x_long = __shfl_sync(0xffffffffu, x_long, lane & ~3);
+      tail_at = __shfl_sync(0xffffffffu, tail_at, lane & ~3);
+      if (PB != 0) {  // private columns: the 4 lanes of a chunk fill their own copy in parallel
+        nsym = __shfl_sync(0xffffffffu, nsym, lane & ~3);
+        if (active && hsize >= 0)
+          fill_lut_col<(PB ? PB : 5)>(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + lane, S.tail() + tail_at, stream == 0, weights, nsym, lg);
+      }
+      __syncwarp();  // the ring and the stage (aliased by the parse scratch) are free from here on
     }
-    if (!ok) {
+    // From here on no lane leaves early: the output flush is a warp-wide exchange.
+    bool live = active && hsize >= 0;
+
+    // ---- jump table (huf_decompress.c:283-290) ----
+    const uint8_t* p = cfg.body + d.src_off + (live ? hsize : 0);
+    const uint32_t rest = live ? d.src_len - (uint32_t)hsize : 0;
+    uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    if (live) {
+      bool ok = rest >= 10;
+      if (ok) {
+        l0 = p[0] | (p[1] << 8);
+        l1 = p[2] | (p[3] << 8);
+        l2 = p[4] | (p[5] << 8);
+        ok = l0 + l1 + l2 + 6 <= rest;
+        l3 = rest - (l0 + l1 + l2 + 6);
+        ok = ok && l0 && l1 && l2 && l3;
+      }
+      if (!ok) {
+        atomicOr(&cfg.ctrl->error, kErrCorrupt);
+        live = false;
+      }
+    }
+    const uint32_t seg = d.dec_len >> 2;  // fused chunks: dec_len % 128 == 0
+    uint32_t s_off = 6, s_len = l0;
+    if (stream == 1) { s_off += l0; s_len = l1; }
+    if (stream == 2) { s_off += l0 + l1; s_len = l2; }
+    if (stream == 3) { s_off += l0 + l1 + l2; s_len = l3; }
+    const uint32_t out_off = (uint32_t)stream * seg;
+
+    LUT lut;
+    if constexpr (PB == 0) {
+      lut.prim_s = S.base_s + S.table_off + 512u * (uint32_t)slot;
+    } else {
+      lut.col_s = S.base_s + S.table_off + 2u * (uint32_t)lane;
+    }
+    lut.tail_s = S.base_s + S.tail_off + 2u * tail_at;
+    lut.x_long = (uint32_t)x_long;
+
+    // ---- which way do the other planes and the output travel?  (warp-uniform) ----
+    // Bulk tensor copies need all 32 lanes live on full chunks and every other plane stored raw at its
+    // predicted place (cfg.side_pred: all groups in front of it raw, which the host cannot know).
+    bool regular = live && c < cfg.k_full;
+    if (G > 1 && regular) {
+#pragma unroll
+      for (int g = 0; g < G - 1; g++) {
+        const ItemDesc t = cfg.items[(uint64_t)g * K + c];
+        regular = regular && t.kind == kRaw && t.src_off == cfg.side_pred[g] + c * (uint64_t)(cfg.chunk / (uint32_t)G);
+      }
+    }
+    regular = __all_sync(0xffffffffu, regular);
+    const bool out_tma = regular && (cfg.tma_flags & kTmaOut);
+
+    BitWindow b;
+    if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring()[lane])) {
       atomicOr(&cfg.ctrl->error, kErrCorrupt);
       live = false;
     }
-  }
-  const uint32_t seg = d.dec_len >> 2;  // fused chunks: dec_len % 128 == 0
-  uint32_t s_off = 6, s_len = l0;
-  if (stream == 1) { s_off += l0; s_len = l1; }
-  if (stream == 2) { s_off += l0 + l1; s_len = l2; }
-  if (stream == 3) { s_off += l0 + l1 + l2; s_len = l3; }
-  const uint32_t out_off = (uint32_t)stream * seg;
+    // (a lane that drops out here only happens on a corrupt stream; `regular` groups keep going with the
+    //  lane decoding garbage from its zeroed window -- the error bit is already set, the output is discarded)
+    if (regular && !live) {
+      b.cont = 0; b.s = 53; b.qm = 0; b.next = 0; b.fetch = 0; b.floor_off = 0xffffffffu; b.start_bit = 0;
+      b.ring = S.ring()[lane];
+      b.ring_s = (uint32_t)__cvta_generic_to_shared(b.ring);
+      b.gbase = cfg.body;
+    }
 
-  // ---- the other planes: groups 0 .. G-2 ----
-  constexpr int NS = (G > 1) ? G - 1 : 1;
-  SidePlane side[NS];
-  const uint4* hi_block = reinterpret_cast<const uint4*>(((uintptr_t)(cfg.body + cfg.body_len) - 1) & ~(uintptr_t)15);
-  if (G > 1 && live) {
+    const uint32_t rows_full = (seg >> 4) / kIters;
+    // ================= cp.async / LDS + STG path =================
+    // ---- the other planes: groups 0 .. G-2 ----
+    SidePlane side[NS];
+    if (G > 1 && live) {
 #pragma unroll
-    for (int g = 0; g < G - 1; g++) {
-      const uint64_t i = (uint64_t)g * K + c;
-      const ItemDesc t = cfg.items[i];
-      const uint8_t* q;
-      if (t.kind == kRle) {
-        q = cfg.fill + i * kFillBytes;
-        side[g].step = 0;
-      } else {
-        q = cfg.body + t.src_off + out_off;
-        side[g].step = 1;
+      for (int g = 0; g < G - 1; g++) {
+        const uint64_t i = (uint64_t)g * K + c;
+        const ItemDesc t = cfg.items[i];
+        const uint8_t* q;
+        if (t.kind == kRle) {
+          q = cfg.fill + i * kFillBytes;
+          side[g].step = 0;
+        } else {
+          q = cfg.body + t.src_off + out_off;
+          side[g].step = 1;
+        }
+        side[g].shift = (uint32_t)((uintptr_t)q & 15);
+        side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
+        side[g].a = ldg128(side[g].blk);
+        const uint4* nb = side[g].blk + side[g].step;
+        side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
+        nb += side[g].step;
+        // block 2 waits in slot 0 (committed and waited for by the first decode16 group)
+        side[g].swz = kSideSlots == 2 ? (((uint32_t)lane >> 2) & 1u) : (((uint32_t)lane >> 1) & 3u);
+        side[g].slots_s = side_slots_s<G, PB>(S, g) + 16u * kSideSlots * (uint32_t)lane;
+        cp_async16_s(side_slot(side[g], 2u), (side[g].step && nb > hi_block) ? hi_block : nb);
       }
-      side[g].shift = (uint32_t)((uintptr_t)q & 15);
-      side[g].blk = reinterpret_cast<const uint4*>((uintptr_t)q & ~(uintptr_t)15);
-      side[g].a = ldg128(side[g].blk);
-      const uint4* nb = side[g].blk + side[g].step;
-      side[g].b = ldg128((side[g].step && nb > hi_block) ? hi_block : nb);
-      nb += side[g].step;
-      // block 2 waits in slot 2 (the window setup below commits and waits for it)
-      side[g].swz = ((uint32_t)lane >> 1) & 3u;
-      side[g].slots_s = (uint32_t)__cvta_generic_to_shared(S.side) + 64u * (uint32_t)(32 * g + lane);
-      cp_async16_s(side_slot(side[g], 2u), (side[g].step && nb > hi_block) ? hi_block : nb);
+      cp_async_commit();
+      cp_async_wait<0>();
     }
-  }
 
-  const bool rot = (cfg.bits_mode == 1) && (G > 1);
-  LUT lut;
-  if constexpr (PB == 0) {
-    lut.prim_s = (uint32_t)__cvta_generic_to_shared(S.prim[slot]);
-  } else {
-    lut.col_s = (uint32_t)__cvta_generic_to_shared(smem_raw) + col_off + 2u * (uint32_t)lane;
-  }
-  lut.tail_s = (uint32_t)__cvta_generic_to_shared(S.tail + tail_at);
-  lut.x_long = (uint32_t)x_long;
-  BitWindow b;
-  if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring[lane])) {
-    atomicOr(&cfg.ctrl->error, kErrCorrupt);
-    live = false;
-  }
-
-  // ---- rows: 128 bytes of output = 128/G elements = kIters iterations of 16 symbols ----
-  constexpr int kIters = 8 / G;
-  const uint32_t my_rows = live ? (seg >> 4) / kIters : 0;
-  uint32_t max_rows = my_rows;
+    // ---- rows: 128 bytes of output = 128/G elements = kIters iterations of 16 symbols ----
+    const uint32_t my_rows = live ? rows_full : 0;
+    uint32_t max_rows = my_rows;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) max_rows = max(max_rows, __shfl_xor_sync(0xffffffffu, max_rows, o));
-  // the 8 stage rows this lane writes out each round: row r*4 + lane/8, 16-byte unit lane%8
-  const uint64_t my_out = (uint64_t)(uintptr_t)(out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G);
-  uint64_t row_out[8];
-  uint32_t row_cnt[8];
+    for (int o = 16; o; o >>= 1) max_rows = max(max_rows, __shfl_xor_sync(0xffffffffu, max_rows, o));
+    if (out_tma) {
+      const uint32_t y0 = (uint32_t)(grp * 32u);
+      for (uint32_t row = 0; row < max_rows; row++) {
+        const bool guard = row + 2 >= my_rows;
 #pragma unroll
-  for (int r = 0; r < 8; r++) {
-    const int src = r * 4 + (lane >> 3);
-    row_out[r] = __shfl_sync(0xffffffffu, my_out, src) + (uint64_t)(lane & 7) * 16;
-    row_cnt[r] = __shfl_sync(0xffffffffu, my_rows, src);
-  }
-
-  for (uint32_t row = 0; row < max_rows; row++) {
-    if (row < my_rows) {
-      const bool guard = row + 2 >= my_rows;  // look-ahead of 3 blocks: clamp in the last two rows
-      // unrolled: with it = row * kIters + k the slot phases (it + 2) & 3, (it + 3) & 3 fold to constants for
-      // the 16-bit types (kIters = 4)
+        for (int k = 0; k < kIters; k++)
+          fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, stage, lane, k * G, row * (uint32_t)kIters + (uint32_t)k, k == 0 && store_pending);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&maps.out, stage_s, row * 128u, y0);
+        store_pending = true;
+      }
+    } else {
+      // the 8 stage rows this lane writes out each round: row r*4 + lane/8, 16-byte unit lane%8
+      const uint64_t my_out = (uint64_t)(uintptr_t)(out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G);
+      uint64_t row_out[8];
+      uint32_t row_cnt[8];
 #pragma unroll
-      for (int k = 0; k < kIters; k++)
-        fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, S.stage, lane, k * G, row * (uint32_t)kIters + (uint32_t)k);
-    }
-    __syncwarp();
+      for (int r = 0; r < 8; r++) {
+        const int src = r * 4 + (lane >> 3);
+        row_out[r] = __shfl_sync(0xffffffffu, my_out, src) + (uint64_t)(lane & 7) * 16;
+        row_cnt[r] = __shfl_sync(0xffffffffu, my_rows, src);
+      }
+      if (store_pending) {
+        if (lane == 0) tma_store_wait_read();
+        store_pending = false;
+        __syncwarp();
+      }
+      for (uint32_t row = 0; row < max_rows; row++) {
+        if (row < my_rows) {
+          const bool guard = row + 2 >= my_rows;  // look-ahead of 3 blocks: clamp in the last two rows
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-      const int src = r * 4 + (lane >> 3);
-      if (row < row_cnt[r]) {
-        const uint4 v = *stage_unit(S.stage, src, lane & 7);
-        *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
+          for (int k = 0; k < kIters; k++)
+            fused_iteration<G, LUT>(b, lut, side, hi_block, guard, rot, stage, lane, k * G, row * (uint32_t)kIters + (uint32_t)k, false);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const int src = r * 4 + (lane >> 3);
+          if (row < row_cnt[r]) {
+            const uint4 v = *stage_unit(stage, src, lane & 7);
+            *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
+          }
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
+    if (live && !window_exact(b)) atomicOr(&cfg.ctrl->error, kErrCorrupt);
   }
-  if (live && !window_exact(b)) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+  if (store_pending && lane == 0) tma_store_wait_all();  // the stage must outlive the last bulk store's reads
 }
 
 // ====================================================================================
@@ -990,86 +1261,160 @@ __device__ __forceinline__ uint8_t plane_byte(const PlaneSrc& s, uint32_t j) {
 constexpr int kMergeThreads = 256;
 constexpr uint32_t kMergeTile = kMergeThreads * 16 * 4;  // bytes of output per block step (16 KiB)
 
+// One 16 KiB output tile of chunk c, by the kMergeThreads threads of a CTA.  `pslot` = the chunk's plane slot.
 template <int G>
-__global__ void __launch_bounds__(kMergeThreads) k_regroup(DecodeCfg cfg, uint8_t* __restrict__ out) {
-  __shared__ PlaneSrc src[G];
+__device__ __forceinline__ void regroup_tile(const DecodeCfg& cfg, uint8_t* __restrict__ out, uint64_t c, uint32_t tile, uint32_t pslot,
+                                             PlaneSrc (&src)[G]) {
   const uint64_t K = cfg.K;
   const uint32_t chunk = cfg.chunk;
-  const uint32_t tiles_per_chunk = (chunk + kMergeTile - 1) / kMergeTile;
-  const uint64_t ntiles = (uint64_t)cfg.ctrl->regroup_count * tiles_per_chunk;  // usually none: the fused kernel wrote everything
-  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const uint64_t c = cfg.rlist[t / tiles_per_chunk];
-    const uint32_t tile = (uint32_t)(t % tiles_per_chunk);
-    const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)chunk) : chunk;
-    const uint32_t o_begin = tile * kMergeTile;
-    if (o_begin >= chunk_len) continue;
-    __syncthreads();
-    if (threadIdx.x < G) {
-      const int g = threadIdx.x;
-      const ItemDesc d = cfg.items[(uint64_t)g * K + c];
-      PlaneSrc s;
-      s.len = d.dec_len;
-      s.fill = 0;
-      if (d.kind == kRaw) {
-        s.ptr = cfg.body + d.src_off;
-      } else if (d.kind == kRle) {
-        s.ptr = nullptr;
-        s.fill = 0x01010101u * (uint32_t)cfg.body[d.src_off];
-      } else {
-        s.ptr = cfg.planes + ((uint64_t)cfg.slot[c] * G + g) * cfg.pstride;
-      }
-      src[g] = s;
+  const uint32_t chunk_len = (c == K - 1) ? (uint32_t)(cfg.orig - c * (uint64_t)chunk) : chunk;
+  const uint32_t o_begin = tile * kMergeTile;
+  if (o_begin >= chunk_len) return;  // (uniform across the CTA)
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    const ItemDesc d = cfg.items[(uint64_t)g * K + c];
+    PlaneSrc s;
+    s.len = d.dec_len;
+    s.fill = 0;
+    if (d.kind == kRaw) {
+      s.ptr = cfg.body + d.src_off;
+    } else if (d.kind == kRle) {
+      s.ptr = nullptr;
+      s.fill = 0x01010101u * (uint32_t)cfg.body[d.src_off];
+    } else {
+      s.ptr = cfg.planes + ((uint64_t)pslot * G + g) * cfg.pstride;
     }
-    __syncthreads();
-    uint8_t* out_c = out + c * (uint64_t)chunk;
-    const uint32_t o_end = min(chunk_len, o_begin + kMergeTile);
-    const uint32_t rot_words = (cfg.bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;  // words that get un-rotated
-    for (uint32_t o = o_begin + threadIdx.x * 16; o < o_end; o += kMergeThreads * 16) {
-      if (o + 16 <= o_end) {
-        uint32_t r[4];
-        if (G == 1) {
-          load_plane_words<4>(src[0], o, r);
-        } else if (G == 2) {
-          uint32_t a[2], b2[2];
-          load_plane_words<2>(src[0], o >> 1, a);
-          load_plane_words<2>(src[1 % G], o >> 1, b2);
-          r[0] = __byte_perm(a[0], b2[0], 0x5140);
-          r[1] = __byte_perm(a[0], b2[0], 0x7362);
-          r[2] = __byte_perm(a[1], b2[1], 0x5140);
-          r[3] = __byte_perm(a[1], b2[1], 0x7362);
-        } else {
-          uint32_t p0[1], p1[1], p2[1], p3[1];
-          load_plane_words<1>(src[0], o >> 2, p0);
-          load_plane_words<1>(src[1 % G], o >> 2, p1);
-          load_plane_words<1>(src[2 % G], o >> 2, p2);
-          load_plane_words<1>(src[3 % G], o >> 2, p3);
-          const uint32_t t0 = __byte_perm(p0[0], p1[0], 0x5140), t1 = __byte_perm(p2[0], p3[0], 0x5140);
-          const uint32_t t2 = __byte_perm(p0[0], p1[0], 0x7362), t3 = __byte_perm(p2[0], p3[0], 0x7362);
-          r[0] = __byte_perm(t0, t1, 0x5410);
-          r[1] = __byte_perm(t0, t1, 0x7632);
-          r[2] = __byte_perm(t2, t3, 0x5410);
-          r[3] = __byte_perm(t2, t3, 0x7632);
-        }
-        const uint32_t w0 = o >> 2;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-          if (w0 + i < rot_words) r[i] = unrot_word<G>(r[i]);
-        *reinterpret_cast<uint4*>(out_c + o) = make_uint4(r[0], r[1], r[2], r[3]);
+    src[g] = s;
+  }
+  __syncthreads();
+  uint8_t* out_c = out + c * (uint64_t)chunk;
+  const uint32_t o_end = min(chunk_len, o_begin + kMergeTile);
+  const uint32_t rot_words = (cfg.bits_mode == 1 && G > 1) ? (chunk_len >> 2) : 0;  // words that get un-rotated
+  for (uint32_t o = o_begin + threadIdx.x * 16; o < o_end; o += kMergeThreads * 16) {
+    if (o + 16 <= o_end) {
+      uint32_t r[4];
+      if (G == 1) {
+        load_plane_words<4>(src[0], o, r);
+      } else if (G == 2) {
+        uint32_t a[2], b2[2];
+        load_plane_words<2>(src[0], o >> 1, a);
+        load_plane_words<2>(src[1 % G], o >> 1, b2);
+        r[0] = __byte_perm(a[0], b2[0], 0x5140);
+        r[1] = __byte_perm(a[0], b2[0], 0x7362);
+        r[2] = __byte_perm(a[1], b2[1], 0x5140);
+        r[3] = __byte_perm(a[1], b2[1], 0x7362);
       } else {
-        // ragged tail of the last chunk: byte by byte, whole words still get un-rotated
-        for (uint32_t q = o; q < min(o + 16, o_end); q += 4) {
-          uint32_t w = 0;
-          const uint32_t nb = min(4u, o_end - q);
-          for (uint32_t i = 0; i < nb; i++) {
-            const uint32_t pos = q + i;
-            w |= (uint32_t)plane_byte(src[pos % G], pos / G) << (8 * i);
-          }
-          if ((q >> 2) < rot_words) w = unrot_word<G>(w);
-          for (uint32_t i = 0; i < nb; i++) out_c[q + i] = (uint8_t)(w >> (8 * i));
+        uint32_t p0[1], p1[1], p2[1], p3[1];
+        load_plane_words<1>(src[0], o >> 2, p0);
+        load_plane_words<1>(src[1 % G], o >> 2, p1);
+        load_plane_words<1>(src[2 % G], o >> 2, p2);
+        load_plane_words<1>(src[3 % G], o >> 2, p3);
+        const uint32_t t0 = __byte_perm(p0[0], p1[0], 0x5140), t1 = __byte_perm(p2[0], p3[0], 0x5140);
+        const uint32_t t2 = __byte_perm(p0[0], p1[0], 0x7362), t3 = __byte_perm(p2[0], p3[0], 0x7362);
+        r[0] = __byte_perm(t0, t1, 0x5410);
+        r[1] = __byte_perm(t0, t1, 0x7632);
+        r[2] = __byte_perm(t2, t3, 0x5410);
+        r[3] = __byte_perm(t2, t3, 0x7632);
+      }
+      const uint32_t w0 = o >> 2;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (w0 + i < rot_words) r[i] = unrot_word<G>(r[i]);
+      *reinterpret_cast<uint4*>(out_c + o) = make_uint4(r[0], r[1], r[2], r[3]);
+    } else {
+      // ragged tail of the last chunk: byte by byte, whole words still get un-rotated
+      for (uint32_t q = o; q < min(o + 16, o_end); q += 4) {
+        uint32_t w = 0;
+        const uint32_t nb = min(4u, o_end - q);
+        for (uint32_t i = 0; i < nb; i++) {
+          const uint32_t pos = q + i;
+          w |= (uint32_t)plane_byte(src[pos % G], pos / G) << (8 * i);
         }
+        if ((q >> 2) < rot_words) w = unrot_word<G>(w);
+        for (uint32_t i = 0; i < nb; i++) out_c[q + i] = (uint8_t)(w >> (8 * i));
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(kMergeThreads) k_regroup_batch(BatchCfg B) {
+  __shared__ PlaneSrc src[4];
+  const uint64_t total = B.tile_start[B.n];
+  for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const uint32_t t = batch_find(B.tile_start, B.n, w);
+    const DecodeCfg& cfg = B.cfgs[t];
+    const uint32_t tiles_per_chunk = (cfg.chunk + kMergeTile - 1) / kMergeTile;
+    const uint64_t local = w - B.tile_start[t];
+    if (local >= (uint64_t)cfg.ctrl->regroup_count * tiles_per_chunk) continue;  // (uniform)
+    const uint64_t c = cfg.rlist[local / tiles_per_chunk];
+    const uint32_t tile = (uint32_t)(local % tiles_per_chunk);
+    if (cfg.G == 1) regroup_tile<1>(cfg, cfg.out, c, tile, cfg.slot[c], reinterpret_cast<PlaneSrc (&)[1]>(src));
+    else if (cfg.G == 2) regroup_tile<2>(cfg, cfg.out, c, tile, cfg.slot[c], reinterpret_cast<PlaneSrc (&)[2]>(src));
+    else regroup_tile<4>(cfg, cfg.out, c, tile, cfg.slot[c], src);
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kMergeThreads) k_regroup(DecodeCfg cfg, uint8_t* __restrict__ out) {
+  __shared__ PlaneSrc src[G];
+  const uint32_t tiles_per_chunk = (cfg.chunk + kMergeTile - 1) / kMergeTile;
+  const uint64_t ntiles = (uint64_t)cfg.ctrl->regroup_count * tiles_per_chunk;  // usually none: the fused kernel wrote everything
+  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const uint64_t c = cfg.rlist[t / tiles_per_chunk];
+    regroup_tile<G>(cfg, out, c, (uint32_t)(t % tiles_per_chunk), cfg.slot[c], src);
+  }
+}
+
+// ====================================================================================
+// Kernel 4: general chunks beyond the slot pool.  kOverflowCtas persistent CTAs, each owning the
+// plane slot max_slots + blockIdx.x: warp 0 decodes the chunk's coded planes (one lane per
+// bitstream, G x 4 <= 16 of them), then the whole CTA regroups the chunk and takes the next
+// one.  Costs nothing when the queue is empty (the normal case).
+// ====================================================================================
+template <int G>
+__device__ __forceinline__ void decode_overflow_body(const DecodeCfg& cfg, uint8_t* __restrict__ out, DecodeSmem& S, PlaneSrc (&src)[G]) {
+  const uint32_t n = cfg.ctrl->overflow_count;
+  const uint32_t pslot = cfg.max_slots + blockIdx.x;
+  const uint32_t tiles_per_chunk = (cfg.chunk + kMergeTile - 1) / kMergeTile;
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint64_t c = cfg.olist[i];
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x, slot = lane >> 2, stream = lane & 3;
+      ItemDesc d;
+      d.kind = kRaw;
+      d.src_off = 0;
+      d.src_len = d.dec_len = 0;
+      bool active = false;
+      if (slot < G) {
+        d = cfg.items[(uint64_t)slot * cfg.K + c];
+        active = (d.kind == kHuf);
+      }
+      planar_decode_item(S, cfg, d, active, slot, stream, cfg.planes + ((uint64_t)pslot * G + (slot < G ? slot : 0)) * cfg.pstride);
+    }
+    __threadfence_block();
+    __syncthreads();  // the planes are complete
+    for (uint32_t tile = 0; tile < tiles_per_chunk; tile++) regroup_tile<G>(cfg, out, c, tile, pslot, src);
+    __syncthreads();  // ... and read, before the next chunk overwrites them
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kMergeThreads) k_decode_overflow(DecodeCfg cfg, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ PlaneSrc src[G];
+  decode_overflow_body<G>(cfg, out, *reinterpret_cast<DecodeSmem*>(smem_raw), src);
+}
+// grid = (kOverflowCtas, tensors)
+__global__ void __launch_bounds__(kMergeThreads) k_decode_overflow_batch(BatchCfg B) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ PlaneSrc src[4];
+  const DecodeCfg& cfg = B.cfgs[blockIdx.y];
+  if (blockIdx.x >= cfg.ovf_slots || cfg.ctrl->overflow_count == 0) return;
+  DecodeSmem& S = *reinterpret_cast<DecodeSmem*>(smem_raw);
+  if (cfg.G == 1) decode_overflow_body<1>(cfg, cfg.out, S, reinterpret_cast<PlaneSrc (&)[1]>(src));
+  else if (cfg.G == 2) decode_overflow_body<2>(cfg, cfg.out, S, reinterpret_cast<PlaneSrc (&)[2]>(src));
+  else decode_overflow_body<4>(cfg, cfg.out, S, src);
 }
 
 }  // namespace zb

@@ -1,0 +1,375 @@
+// decode_sync.cuh -- intra-stream parallel Huffman decode for small and medium tensors.
+//
+// k_huf_decode_fused gives every huff0 bitstream ONE thread (huf_decompress.c:203-260 is a serial
+// loop: symbol i+1 starts where symbol i ends), so a decode takes ~2 ms whether the tensor has 4
+// chunks or 20 000.  Huffman codes self-synchronise: a decoder started at a wrong bit position
+// falls into step with the true parse after a few symbols.  This kernel uses that (Klein & Wiseman;
+// Weissenberger & Schmidt for GPUs), with the reference's stream format untouched:
+//
+//   one CTA = one bitstream of one coded item; the stream's bits are cut into one segment per
+//   thread;
+//   1. every thread decodes from its segment start (a guess, except thread 0) to the segment's
+//      lower bound and publishes where it stopped -- a code boundary just beyond the bound -- and
+//      how many symbols it saw;
+//   2. every thread takes its predecessor's stop as its start; whoever's start changed decodes
+//      again; repeat until nothing changes.  Thread 0 is right from the beginning and each round
+//      makes at least one more thread right, so this ends; in practice after 2 rounds, because a
+//      stop is right as soon as the parse synchronised anywhere inside the segment;
+//   3. a block-wide prefix sum of the symbol counts gives each thread its output offset; the
+//      total must be the stream's symbol count and the last stop the stream's first bit
+//      (huf_decompress.c:348-349);
+//   4. every thread decodes its segment once more, now writing into the quarter plane in shared
+//      memory;
+//   5. the CTA merges the quarter plane with the matching bytes of the other planes (+ sign-bit
+//      un-rotate) and writes elements with coalesced 128-bit stores -- or, for chunks that need
+//      the general regroup (several coded groups, ragged tail), copies the quarter plane to the
+//      chunk's workspace plane.
+// About 2.6 decode passes instead of 1, but over 256 threads per bitstream instead of 1: a 1 MiB
+// tensor is 16 CTAs x ~20 us instead of 16 threads x 1.5 ms.  One full 2^11-entry table per CTA
+// (built by 256 threads), so no two-level lookup.
+#pragma once
+#include "decode.cuh"
+
+namespace zb {
+
+constexpr int kSyncThreads = 256;
+constexpr uint32_t kSyncMinSegBits = 192;  // shorter segments only add overshoot work
+
+struct SyncShared {
+  uint16_t lut[kDecLutEntries];                    // full table: symbol | (-length << 8), replicated into 11 bits
+  __align__(16) uint8_t ring[kSyncThreads][kRingBytes];
+  uint32_t stop[kSyncThreads];                     // bit offset where segment m's decode stopped
+  uint32_t count[kSyncThreads];                    // symbols of segment m; then their exclusive prefix
+  uint32_t warp_tot[kSyncThreads / 32];
+  uint8_t weights[256];
+  int lg, hsize, nsym;
+  uint32_t cls_start[kHufLogMax + 2];              // index-space start of weight class w (11-bit space)
+  uint32_t cls_count[kHufLogMax + 2];
+  PlaneSrc src[4];
+  __align__(16) uint8_t plane[kHufBlockMax / 4 + 16];  // the decoded quarter plane; the tANS scratch of the parse aliases it
+};
+static_assert(sizeof(FseDec) <= kHufBlockMax / 4, "the parse scratch aliases the plane");
+
+// Symbols of the quarter plane [i0, i0 + 4*NW) as words (4 symbols each).
+template <int NW>
+__device__ __forceinline__ void smem_plane_words(const uint8_t* plane, uint32_t i0, uint32_t (&out)[NW]) {
+#pragma unroll
+  for (int i = 0; i < NW; i++) out[i] = *reinterpret_cast<const uint32_t*>(plane + i0 + 4 * i);
+}
+
+// One symbol; `rem` counts the bits left above the segment's lower bound.
+template <class LUT>
+__device__ __forceinline__ uint32_t sync_decode(BitWindow& b, const LUT& lut, int32_t& rem) {
+  const uint32_t x = (uint32_t)(b.cont >> b.s);
+  const int32_t e = lut.get(x);
+  b.s += e >> 8;
+  rem += e >> 8;
+  return (uint32_t)e;
+}
+
+// Decode from bit offset `from` down to the first code boundary at or below `bound`.
+// -> symbols seen; `stop` = that boundary.
+__device__ __forceinline__ uint32_t sync_scan(BitWindow& b, const LutFull& lut, uint32_t from, uint32_t bound, uint32_t& stop) {
+  int32_t rem = (int32_t)(from - bound);
+  uint32_t n = 0;
+  if (rem > 0) {
+    window_seek(b, from);
+    for (;;) {
+      ring_top_up(b, 1);
+      cp_async_commit();
+      bool done = false;
+#pragma unroll
+      for (int k = 0; k < 4 && !done; k++) {
+        window_refill(b);
+        sync_decode(b, lut, rem);
+        n++;
+        if (rem <= 0) {
+          done = true;
+          break;
+        }
+        sync_decode(b, lut, rem);
+        n++;
+        if (rem <= 0) done = true;
+      }
+      cp_async_wait<1>();
+      if (done) break;
+    }
+    cp_async_wait<0>();
+  }
+  stop = (uint32_t)((int32_t)bound + rem);
+  return n;
+}
+
+// Decode exactly `n` symbols from bit offset `from` into plane[off ..): whole words where the
+// thread owns all four bytes, single bytes at its two ends.
+__device__ __forceinline__ void sync_emit(BitWindow& b, const LutFull& lut, uint32_t from, uint32_t n, uint8_t* plane, uint32_t off) {
+  if (n == 0) return;
+  window_seek(b, from);
+  int32_t dummy = 0;
+  uint32_t pos = off, acc = 0;
+  const uint32_t end = off + n;
+  while (pos < end) {
+    ring_top_up(b, 1);
+    cp_async_commit();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (pos < end) {
+        if ((k & 1) == 0) window_refill(b);
+        const uint32_t sym = sync_decode(b, lut, dummy) & 0xFFu;
+        acc |= sym << ((pos & 3u) * 8u);
+        pos++;
+        if ((pos & 3u) == 0) {
+          if (pos - 4 >= off) {
+            *reinterpret_cast<uint32_t*>(plane + pos - 4) = acc;
+          } else {
+            for (uint32_t q = off; q < pos; q++) plane[q] = (uint8_t)(acc >> ((q & 3u) * 8u));
+          }
+          acc = 0;
+        }
+      }
+    }
+    cp_async_wait<1>();
+  }
+  cp_async_wait<0>();
+  if (pos & 3u) {
+    const uint32_t w0 = pos & ~3u;
+    for (uint32_t q = (w0 > off ? w0 : off); q < pos; q++) plane[q] = (uint8_t)(acc >> ((q & 3u) * 8u));
+  }
+}
+
+// items: hlist[0 .. ctrl->huf_count) = coded items (g * K + c) of chunks in fused or general mode.
+// One bitstream: work = 4 * (index into hlist) + stream.  The caller has synchronised the CTA since
+// the previous call (the shared state is reused).
+template <int G>
+__device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __restrict__ out, SyncShared& S, uint64_t work) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint64_t K = cfg.K;
+  {
+    const uint64_t item = cfg.hlist[work >> 2];
+    const int stream = (int)(work & 3);
+    const int g = (int)(item / K);
+    const uint64_t c = item - (uint64_t)g * K;
+    const ItemDesc d = cfg.items[item];
+    const uint32_t mode = cfg.mode[c];
+
+    // ---- table description -> weights (one thread; <= 255 serial tANS steps) ----
+    if (tid == 0) {
+      int nsym = 0, lg = 0;
+      FseDec& D = *reinterpret_cast<FseDec*>(S.plane);
+      int hsize = huf_read_weights(S.weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
+      if (hsize >= 0 && lg > kDecLutLog) {
+        atomicOr(&cfg.ctrl->error, kErrUnsupported);
+        hsize = -1;
+      } else if (hsize < 0) {
+        atomicOr(&cfg.ctrl->error, kErrCorrupt);
+      }
+      S.hsize = hsize;
+      S.nsym = nsym;
+      S.lg = lg;
+      for (int w = 0; w < kHufLogMax + 2; w++) S.cls_count[w] = 0;
+    }
+    __syncthreads();
+    const int hsize = S.hsize, lg = S.lg, nsym = S.nsym;
+    if (hsize < 0) return;  // (uniform)
+    // ---- full table, one thread per symbol (huf_decompress.c:151-183: weights ascending, symbols
+    //      ascending within a weight, 2^(w-1) consecutive entries each) ----
+    int w_mine = 0;
+    uint32_t rank = 0;
+    if (tid < nsym) {
+      w_mine = S.weights[tid];
+      if (w_mine) {
+        for (int m = 0; m < tid; m++) rank += (S.weights[m] == w_mine);
+        atomicAdd(&S.cls_count[w_mine], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t at = 0;
+      for (int w = 1; w <= lg; w++) {
+        S.cls_start[w] = at;
+        at += (S.cls_count[w] << (w - 1)) << (kDecLutLog - lg);
+      }
+    }
+    __syncthreads();
+    if (w_mine) {
+      const int len = lg + 1 - w_mine;
+      const uint32_t span = 1u << (kDecLutLog - len);
+      const uint32_t u = S.cls_start[w_mine] + rank * span;
+      const uint16_t e = (uint16_t)(tid | (((256 - len) & 0xFF) << 8));  // symbol | -length
+      if (span >= 2) {
+        const uint32_t ee = (uint32_t)e | ((uint32_t)e << 16);
+        uint32_t* p = reinterpret_cast<uint32_t*>(S.lut + u);  // u is a multiple of span, so even
+        for (uint32_t q = 0; q < (span >> 1); q++) p[q] = ee;
+      } else {
+        S.lut[u] = e;
+      }
+    }
+    // ---- this CTA's bitstream (jump table, huf_decompress.c:283-290) ----
+    const uint8_t* p = cfg.body + d.src_off + hsize;
+    const uint32_t rest = d.src_len - (uint32_t)hsize;
+    bool ok = rest >= 10;
+    uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    if (ok) {
+      l0 = p[0] | (p[1] << 8);
+      l1 = p[2] | (p[3] << 8);
+      l2 = p[4] | (p[5] << 8);
+      ok = l0 + l1 + l2 + 6 <= rest;
+      l3 = rest - (l0 + l1 + l2 + 6);
+      ok = ok && l0 && l1 && l2 && l3;
+    }
+    const uint32_t seg = (d.dec_len + 3) >> 2;
+    ok = ok && 3 * seg <= d.dec_len;
+    uint32_t s_off = 6, s_len = l0;
+    if (stream == 1) { s_off += l0; s_len = l1; }
+    if (stream == 2) { s_off += l0 + l1; s_len = l2; }
+    if (stream == 3) { s_off += l0 + l1 + l2; s_len = l3; }
+    const uint32_t out_off = (uint32_t)stream * seg;
+    const uint32_t count = ok ? ((stream == 3) ? d.dec_len - 3 * seg : seg) : 0;
+    uint8_t lastb = 0;
+    if (ok) {
+      lastb = p[s_off + s_len - 1];
+      ok = lastb != 0;
+    }
+    if (!ok) {
+      if (tid == 0) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+      return;  // (uniform: every thread computed the same)
+    }
+    __syncthreads();  // table complete
+    BitWindow b;
+    const uint32_t so = window_frame(b, p + s_off, cfg.body, S.ring[tid]);
+    const uint32_t mark = 8u * (so + s_len - 1) + (uint32_t)hb32(lastb);
+    const uint32_t first = b.start_bit;
+    const LutFull lut{S.lut, kDecLutLog};
+    // ---- segments ----
+    const uint32_t bits = mark - first;
+    uint32_t segbits = (bits + kSyncThreads - 1) / kSyncThreads;
+    if (segbits < kSyncMinSegBits) segbits = kSyncMinSegBits;
+    const uint32_t top = (uint64_t)tid * segbits < bits ? mark - (uint32_t)tid * segbits : first;          // guess (exact for tid 0)
+    const uint32_t bound = (uint64_t)(tid + 1) * segbits < bits ? mark - (uint32_t)(tid + 1) * segbits : first;
+    uint32_t from = top, stop = top, n = 0;
+    bool need = true;
+    for (int round = 0; round <= kSyncThreads; round++) {
+      if (need) n = sync_scan(b, lut, from, bound, stop);
+      S.stop[tid] = stop;
+      __syncthreads();
+      const uint32_t nf = tid ? S.stop[tid - 1] : mark;
+      need = nf != from;
+      from = nf;
+      if (!__syncthreads_or(need)) break;
+    }
+    // ---- output offsets; the stream must hold exactly `count` symbols and be consumed exactly ----
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) S.warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kSyncThreads / 32; w++) {
+      const uint32_t v = S.warp_tot[w];
+      if (w < wid) before += v;
+      total += v;
+    }
+    const uint32_t off = before + incl - n;
+    if (total != count || S.stop[kSyncThreads - 1] != first) {
+      if (tid == 0) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+      return;  // (uniform)
+    }
+    sync_emit(b, lut, from, n, S.plane, off);
+    __syncthreads();
+    // ---- quarter plane -> elements, or -> the chunk's workspace plane ----
+    if (mode == kModeFused) {
+      // fused chunks: the coded plane is the top byte plane, dec_len % 128 == 0, every other plane raw or RLE
+      if (tid < G - 1) {
+        const ItemDesc t = cfg.items[(uint64_t)tid * K + c];
+        PlaneSrc s;
+        s.len = t.dec_len;
+        s.fill = 0;
+        if (t.kind == kRle) {
+          s.ptr = nullptr;
+          s.fill = 0x01010101u * (uint32_t)cfg.body[t.src_off];
+        } else {
+          s.ptr = cfg.body + t.src_off;
+        }
+        S.src[tid] = s;
+      }
+      __syncthreads();
+      uint8_t* out_q = out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G;
+      const bool rot = (cfg.bits_mode == 1) && (G > 1);
+      const uint32_t obytes = count * (uint32_t)G;
+      for (uint32_t o = (uint32_t)tid * 16u; o < obytes; o += kSyncThreads * 16u) {
+        uint32_t r[4];
+        if (G == 1) {
+          smem_plane_words<4>(S.plane, o, r);
+        } else if (G == 2) {
+          uint32_t a[2], e2[2];
+          load_plane_words<2>(S.src[0], out_off + (o >> 1), a);
+          smem_plane_words<2>(S.plane, o >> 1, e2);
+          r[0] = __byte_perm(a[0], e2[0], 0x5140);
+          r[1] = __byte_perm(a[0], e2[0], 0x7362);
+          r[2] = __byte_perm(a[1], e2[1], 0x5140);
+          r[3] = __byte_perm(a[1], e2[1], 0x7362);
+        } else {
+          uint32_t p0[1], p1[1], p2[1], p3[1];
+          load_plane_words<1>(S.src[0], out_off + (o >> 2), p0);
+          load_plane_words<1>(S.src[1 % 3], out_off + (o >> 2), p1);
+          load_plane_words<1>(S.src[2 % 3], out_off + (o >> 2), p2);
+          smem_plane_words<1>(S.plane, o >> 2, p3);
+          const uint32_t t0 = __byte_perm(p0[0], p1[0], 0x5140), t1 = __byte_perm(p2[0], p3[0], 0x5140);
+          const uint32_t t2 = __byte_perm(p0[0], p1[0], 0x7362), t3 = __byte_perm(p2[0], p3[0], 0x7362);
+          r[0] = __byte_perm(t0, t1, 0x5410);
+          r[1] = __byte_perm(t0, t1, 0x7632);
+          r[2] = __byte_perm(t2, t3, 0x5410);
+          r[3] = __byte_perm(t2, t3, 0x7632);
+        }
+        if (rot) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) r[i] = unrot_word<G>(r[i]);
+        }
+        *reinterpret_cast<uint4*>(out_q + o) = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+    } else {
+      uint8_t* dst = cfg.planes + ((uint64_t)cfg.slot[c] * G + g) * cfg.pstride + out_off;
+      if (((uintptr_t)dst & 3) == 0) {
+        const uint32_t nw = count >> 2;
+        for (uint32_t i = tid; i < nw; i += kSyncThreads) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(S.plane)[i];
+        for (uint32_t i = (nw << 2) + tid; i < count; i += kSyncThreads) dst[i] = S.plane[i];
+      } else {
+        for (uint32_t i = tid; i < count; i += kSyncThreads) dst[i] = S.plane[i];
+      }
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kSyncThreads) k_huf_decode_sync(DecodeCfg cfg, uint8_t* __restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SyncShared& S = *reinterpret_cast<SyncShared*>(smem_raw);
+  const uint32_t nh = cfg.ctrl->huf_count;
+  for (uint64_t work = blockIdx.x; work < 4ull * nh; work += gridDim.x) {
+    __syncthreads();  // the previous item's shared state is dead
+    sync_process<G>(cfg, out, S, work);
+  }
+}
+
+// Bitstreams of every tensor of a batch in one grid (flat index -> tensor by binary search).
+__global__ void __launch_bounds__(kSyncThreads) k_huf_decode_sync_batch(BatchCfg B) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SyncShared& S = *reinterpret_cast<SyncShared*>(smem_raw);
+  const uint64_t total = B.item_start[B.n];
+  for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const uint32_t t = batch_find(B.item_start, B.n, w);
+    const DecodeCfg& cfg = B.cfgs[t];
+    const uint64_t work = w - B.item_start[t];
+    if (work >= 4ull * cfg.ctrl->huf_count) continue;  // (uniform) the bound counts every item, only the coded ones are queued
+    __syncthreads();
+    if (cfg.G == 1) sync_process<1>(cfg, cfg.out, S, work);
+    else if (cfg.G == 2) sync_process<2>(cfg, cfg.out, S, work);
+    else sync_process<4>(cfg, cfg.out, S, work);
+  }
+}
+
+}  // namespace zb

@@ -4,15 +4,18 @@
 //              -Xcompiler -fPIC -shared -o libzipnn_b200.so zipnn_b200.cu
 #include "../../include/zipnn_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
 
 #include "common.cuh"
 #include "decode.cuh"
+#include "decode_sync.cuh"
 #include "encode.cuh"
 #include "stage1.cuh"
 
@@ -44,9 +47,9 @@ inline bool cuda_ok(cudaError_t e) {
 // Off by default.  bench.py turns it on to attribute the step time to kernels; the events
 // sit between launches on the same stream, so they do not change the schedule.
 enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKHufDecodePlanar, kKRegroup, kKEncodeStats, kKEncodeTable, kKEncodeScan, kKEncodeWrite, kKEncodeWriteRagged, kKSplit,
-                kKRegroupPlanar, kKCount };
+                kKRegroupPlanar, kKDecodeOverflow, kKHufDecodeSync, kKCount };
 const char* const kKernelNames[kKCount] = {"k_decode_meta", "k_huf_decode_fused", "k_huf_decode_planar", "k_regroup", "k_encode_hist", "k_encode_table",
-                                           "k_encode_scan", "k_encode_write_warp", "k_encode_write_ragged", "k_split_planar", "k_regroup_planar"};
+                                           "k_encode_scan", "k_encode_write_warp", "k_encode_write_ragged", "k_split_planar", "k_regroup_planar", "k_decode_overflow", "k_huf_decode_sync"};
 struct TimedSpan {
   int id;
   cudaEvent_t a, b;
@@ -100,6 +103,58 @@ int sm_count_cached() {
   return cached;
 }
 
+// ---- tensor maps (TMA descriptors) ------------------------------------------------------
+// cuTensorMapEncodeTiled lives in the driver; taken through the runtime so that the library
+// links against nothing but cudart.  A driver without it only costs the fused decode kernel
+// its bulk-copy path.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    (void)cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// bytes viewed as {inner, rows} with a row pitch of `pitch` bytes; box {box_inner, 32}
+bool byte_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch, uint32_t box_inner, CUtensorMapSwizzle sw,
+                 CUtensorMapL2promotion l2) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || ((uintptr_t)base & 15) || (pitch & 15) || inner == 0 || rows == 0 || inner > 0xffffffffull || rows > 0xffffffffull) return false;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch};
+  cuuint32_t box[2] = {box_inner, 32};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Knobs {
+  int tma = 1, grid_mode = 0, warps_per_sm = 0;
+  long long sync_max = -1;  // chunks up to which k_huf_decode_sync replaces the one-thread-per-bitstream kernels (-1: default)
+  size_t smem_pad = 0;
+};
+Knobs knobs() {
+  Knobs k;
+  if (const char* e = getenv("ZIPNN_B200_TMA")) k.tma = atoi(e);
+  if (const char* e = getenv("ZIPNN_B200_GRID_MODE")) k.grid_mode = atoi(e);
+  if (const char* e = getenv("ZIPNN_B200_WARPS_PER_SM")) k.warps_per_sm = atoi(e);
+  if (const char* e = getenv("ZIPNN_B200_SMEM_PAD")) k.smem_pad = (size_t)atoi(e);
+  if (const char* e = getenv("ZIPNN_B200_SYNC_MAX")) k.sync_max = atoll(e);
+  return k;
+}
+
+template <typename Kernel>
+int resident_blocks(Kernel k, size_t smem) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32, smem) != cudaSuccess || nb < 1) nb = 1;
+  return nb;
+}
+
 inline bool valid_layout(int num_buf, int bytes_mode, size_t chunk) {
   if (!(num_buf == 1 || num_buf == 2 || num_buf == 4)) return false;
   // reference: mode 10 for one or two groups (dtype16.c:44,81), 220 for four (dtype32.c:241)
@@ -113,12 +168,17 @@ inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline uint64_t num_chunks(size_t n, size_t chunk) { return (n + chunk - 1) / chunk; }
 
 // ---- decompress workspace layout ----
-//   [Ctrl 256][ItemDesc G*K][mode u8 K][slot u32 K][fill 64*G*K][planes slots*G*pstride]
+//   [Ctrl 256][ItemDesc G*K][mode u8 K][slot u32 K][rlist u32 K][olist u32 K][hlist u32 G*K][fill 64*G*K][planes slots*G*pstride]
 // `planes` is only used by chunks the fused kernel cannot take (several coded groups, or the
-// ragged last chunk); the default size provides kDefaultSlots of them, the "full" size K.
+// ragged last chunk).  The default size provides a pool of kDefaultSlots of them, decoded by
+// whole-GPU kernels, plus kOverflowCtas more that belong to the persistent CTAs of
+// k_decode_overflow, which take every further such chunk: any stream decodes with the default
+// workspace.  The "full" size gives every chunk a pool slot (faster for streams that are all
+// general chunks, e.g. fp32 tensors upcast from bf16).
 constexpr uint64_t kDefaultSlots = 64;
+constexpr uint64_t kSyncDefaultMaxChunks = 3072;  // measured crossover with the one-thread-per-bitstream kernels (768 MiB of 256 KiB chunks)
 struct DecWs {
-  size_t items_off, mode_off, slot_off, rlist_off, fill_off, planes_off, pstride, fixed;
+  size_t items_off, mode_off, slot_off, rlist_off, olist_off, hlist_off, fill_off, planes_off, pstride, fixed;
 };
 inline DecWs dec_ws_layout(size_t orig, int G, size_t chunk) {
   DecWs L;
@@ -127,7 +187,9 @@ inline DecWs dec_ws_layout(size_t orig, int G, size_t chunk) {
   L.mode_off = round_up(L.items_off + sizeof(ItemDesc) * (size_t)G * K, 256);
   L.slot_off = round_up(L.mode_off + K, 256);
   L.rlist_off = round_up(L.slot_off + 4 * K, 256);
-  L.fill_off = round_up(L.rlist_off + 4 * K, 256);
+  L.olist_off = round_up(L.rlist_off + 4 * K, 256);
+  L.hlist_off = round_up(L.olist_off + 4 * K, 256);
+  L.fill_off = round_up(L.hlist_off + 4 * (size_t)G * K, 256);
   L.planes_off = round_up(L.fill_off + (size_t)kFillBytes * G * K, 256);
   L.pstride = round_up(chunk / (size_t)G, 16) + 16;
   L.fixed = L.planes_off + 256;
@@ -219,7 +281,8 @@ int zipnn_b200_decompress_workspace_size(size_t orig, int num_buf, size_t chunk,
   if (!out || chunk == 0 || !(num_buf == 1 || num_buf == 2 || num_buf == 4)) return ZIPNN_B200_E_ARG;
   const DecWs L = dec_ws_layout(orig, num_buf, chunk);
   const uint64_t K = num_chunks(orig, chunk);
-  *out = L.fixed + (size_t)std::min<uint64_t>(K, kDefaultSlots) * num_buf * L.pstride;
+  const uint64_t slots = K <= kDefaultSlots ? K : kDefaultSlots + kOverflowCtas;
+  *out = L.fixed + (size_t)slots * num_buf * L.pstride;
   return ZIPNN_B200_OK;
 }
 
@@ -230,22 +293,16 @@ int zipnn_b200_decompress_workspace_size_full(size_t orig, int num_buf, size_t c
   return ZIPNN_B200_OK;
 }
 
-int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int bits_mode, int bytes_mode,
-                          size_t chunk, size_t orig, void* d_out, void* d_ws, size_t ws_bytes, void* cuda_stream,
-                          int check) {
-  if (!valid_layout(num_buf, bytes_mode, chunk)) return ZIPNN_B200_E_ARG;
-  if (orig == 0) return ZIPNN_B200_OK;
-  if (!d_body || !d_out || !d_ws) return ZIPNN_B200_E_ARG;
-  if (((uintptr_t)d_out & 15) || ((uintptr_t)d_ws & 255)) return ZIPNN_B200_E_ARG;
-  const int G = num_buf;
+// Fill a DecodeCfg for one tensor whose workspace slice is [ws, ws + ws_bytes).
+static int fill_decode_cfg(DecodeCfg& cfg, const void* d_body, size_t body_len, int G, int bits_mode, size_t chunk, size_t orig, void* d_out,
+                           uint8_t* ws, size_t ws_bytes, bool use_sync) {
   const uint64_t K = num_chunks(orig, chunk);
   if (body_len < 9ull * G * K) return ZIPNN_B200_E_CORRUPT;
   const DecWs L = dec_ws_layout(orig, G, chunk);
   if (ws_bytes < L.fixed) return ZIPNN_B200_E_CAPACITY;
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  uint8_t* ws = (uint8_t*)d_ws;
-  DecodeCfg cfg;
+  memset(&cfg, 0, sizeof(cfg));
   cfg.body = (const uint8_t*)d_body;
+  cfg.out = (uint8_t*)d_out;
   cfg.body_len = body_len;
   cfg.G = G;
   cfg.K = K;
@@ -260,8 +317,46 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   cfg.fill = ws + L.fill_off;
   cfg.planes = ws + L.planes_off;
   cfg.pstride = L.pstride;
-  cfg.tail_cap = 0;
-  cfg.max_slots = (uint32_t)std::min<uint64_t>((ws_bytes - L.fixed) / ((size_t)G * L.pstride), K);
+  cfg.olist = (uint32_t*)(ws + L.olist_off);
+  const uint64_t have = (ws_bytes - L.fixed) / ((size_t)G * L.pstride);
+  if (have >= K) {
+    cfg.max_slots = (uint32_t)K;
+    cfg.ovf_slots = 0;
+  } else if (have > kOverflowCtas) {
+    cfg.max_slots = (uint32_t)(have - kOverflowCtas);
+    cfg.ovf_slots = kOverflowCtas;
+  } else {
+    cfg.max_slots = (uint32_t)have;  // a caller-sized scratch below the documented minimum: overflow is an error
+    cfg.ovf_slots = 0;
+  }
+  cfg.hlist = use_sync ? (uint32_t*)(ws + L.hlist_off) : nullptr;
+  return ZIPNN_B200_OK;
+}
+static uint64_t sync_max_chunks() {
+  const Knobs kn = knobs();
+  return kn.sync_max >= 0 ? (uint64_t)kn.sync_max : kSyncDefaultMaxChunks;
+}
+
+int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int bits_mode, int bytes_mode,
+                          size_t chunk, size_t orig, void* d_out, void* d_ws, size_t ws_bytes, void* cuda_stream,
+                          int check) {
+  if (!valid_layout(num_buf, bytes_mode, chunk)) return ZIPNN_B200_E_ARG;
+  if (orig == 0) return ZIPNN_B200_OK;
+  if (!d_body || !d_out || !d_ws) return ZIPNN_B200_E_ARG;
+  if (((uintptr_t)d_out & 15) || ((uintptr_t)d_ws & 255)) return ZIPNN_B200_E_ARG;
+  const int G = num_buf;
+  const uint64_t K = num_chunks(orig, chunk);
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  // Small and medium tensors: one CTA per bitstream (decode_sync.cuh) instead of one thread per bitstream.
+  // The one-thread kernels take ~2.2 ms for anything up to ~20 000 chunks (a bitstream is serial); the
+  // per-bitstream CTAs cost ~K * 0.7 us: crossover near 3000 chunks (measured on B200, profiles/r2c_sweep.txt).
+  const bool use_sync = K <= sync_max_chunks();
+  DecodeCfg cfg;
+  {
+    const int rc = fill_decode_cfg(cfg, d_body, body_len, G, bits_mode, chunk, orig, d_out, (uint8_t*)d_ws, ws_bytes, use_sync);
+    if (rc) return rc;
+  }
+  const Knobs kn = knobs();
   const uint64_t nitems = (uint64_t)G * K;
 
   ZB_CUDA(cudaMemsetAsync(cfg.ctrl, 0, kCtrlBytes, st));
@@ -272,34 +367,85 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     k_decode_meta<<<blocks, threads, 0, st>>>(cfg);
     ZB_LAUNCHED();
   }
-  {
-    const uint64_t warps = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
-    if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
-    // Short-code planes (the exponent plane of the rotated types, ~2.6 bits per symbol) use
-    // conflict-free private 5-bit table columns and a 1024-entry tail pool (8 chunks x ~64 entries
-    // for the codes longer than 5 bits, so 2x slack): 13 KiB per warp with one side plane, 16 warps
-    // per SM.  fp16 / fp8 planes (6-7 bits per symbol, 90-150 entries of > 8 bits per chunk) keep the
-    // shared 8-bit primaries.  A chunk whose tail does not fit the pool takes the general path.
-    const bool short_codes = (G >= 2 && bits_mode == 1);
-    cfg.tail_cap = short_codes ? 1024u : 2048u;
-    ScopedTimer tm(kKHufDecode, st);
+  if (use_sync) {
+    static bool attr_done[5] = {false, false, false, false, false};
     int rc = dispatch_G(G, [&](auto g) -> int {
       constexpr int GG = decltype(g)::value;
-      if (short_codes)
-        k_huf_decode_fused<GG, 5><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 5, GG), st>>>(cfg, (uint8_t*)d_out);
-      else
-        k_huf_decode_fused<GG, 0><<<(unsigned)warps, 32, fused_smem_bytes(cfg.tail_cap, 0, GG), st>>>(cfg, (uint8_t*)d_out);
+      if (!attr_done[GG]) {
+        ZB_CUDA(cudaFuncSetAttribute(k_huf_decode_sync<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncShared)));
+        attr_done[GG] = true;
+      }
+      static const int nb = [] {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_huf_decode_sync<GG>, kSyncThreads, sizeof(SyncShared)) != cudaSuccess || v < 1) v = 1;
+        return v;
+      }();
+      const unsigned grid = (unsigned)std::min<uint64_t>(4 * nitems, (uint64_t)nb * sm_count_cached());
+      ScopedTimer tm(kKHufDecodeSync, st);
+      k_huf_decode_sync<GG><<<grid, kSyncThreads, sizeof(SyncShared), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });
     if (rc) return rc;
-  }
-  {
-    const uint64_t warps = (nitems + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
-    if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
-    ScopedTimer tm(kKHufDecodePlanar, st);
-    k_huf_decode_planar<<<(unsigned)warps, 32, sizeof(DecodeSmem), st>>>(cfg);
-    ZB_LAUNCHED();
+  } else {
+    {
+      const uint64_t groups = (K + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
+      if (groups > 0x7fffffffull) return ZIPNN_B200_E_ARG;
+      // Short-code planes (the exponent plane of the rotated types, ~2.6 bits per symbol) use
+      // conflict-free private 5-bit table columns and a ~1000-entry tail pool (8 chunks x ~64 entries
+      // for the codes longer than 5 bits, so 2x slack).  fp16 / fp8 planes (6-7 bits per symbol, 90-150
+      // entries of > 8 bits per chunk) keep the shared 8-bit primaries.  A chunk whose tail does not
+      // fit the pool takes the general path.
+      const bool short_codes = (G >= 2 && bits_mode == 1);
+      // ---- tensor maps for the bulk-copy path (decode.cuh, "Kernel 2b") ----
+      TmaMaps maps;
+      memset(&maps, 0, sizeof(maps));
+      cfg.tma_flags = 0;
+      cfg.k_full = orig / chunk;
+      const uint64_t last_len = orig - cfg.k_full * chunk;
+      uint64_t at = 9ull * G * K;
+      for (int g = 0; g < 3; g++) {
+        cfg.side_pred[g] = at;
+        cfg.side_r0[g] = (uint32_t)(((uintptr_t)d_body + at) & 15);
+        if (g < G) at += cfg.k_full * (chunk / G) + plane_len((uint32_t)last_len, G, g);
+      }
+      if (cfg.k_full >= (uint64_t)kDecItemsPerWarp && chunk >= 2048 && (chunk / 4) * 4 == chunk) {
+        if (byte_map_2d(&maps.out, d_out, chunk / 4, 4 * cfg.k_full, chunk / 4, 128, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) {
+          cfg.tma_flags |= kTmaOut;
+        }
+      }
+      // tuning knobs for experiments (tools/decode_probe.py); unset in normal use
+      if (!kn.tma) cfg.tma_flags = 0;
+      ScopedTimer tm(kKHufDecode, st);
+      int rc = dispatch_G(G, [&](auto g) -> int {
+        constexpr int GG = decltype(g)::value;
+        const int sms = sm_count_cached();
+        auto grid_for = [&](int nb) -> unsigned {
+          if (kn.grid_mode == 1) return (unsigned)groups;                            // one CTA per chunk group
+          if (kn.warps_per_sm > 0) nb = std::min(nb, kn.warps_per_sm);
+          return (unsigned)std::min<uint64_t>(groups, (uint64_t)nb * sms);          // persistent
+        };
+        if (short_codes) {
+          const size_t smem = fused_smem_bytes<GG>(5) + kn.smem_pad;
+          const int nb = resident_blocks(k_huf_decode_fused<GG, 5>, smem);
+          k_huf_decode_fused<GG, 5><<<grid_for(nb), 32, smem, st>>>(cfg, (uint8_t*)d_out, maps);
+        } else {
+          const size_t smem = fused_smem_bytes<GG>(0) + kn.smem_pad;
+          const int nb = resident_blocks(k_huf_decode_fused<GG, 0>, smem);
+          k_huf_decode_fused<GG, 0><<<grid_for(nb), 32, smem, st>>>(cfg, (uint8_t*)d_out, maps);
+        }
+        ZB_LAUNCHED();
+        return ZIPNN_B200_OK;
+      });
+      if (rc) return rc;
+    }
+    {
+      const uint64_t warps = (nitems + kDecItemsPerWarp - 1) / kDecItemsPerWarp;
+      if (warps > 0x7fffffffull) return ZIPNN_B200_E_ARG;
+      ScopedTimer tm(kKHufDecodePlanar, st);
+      k_huf_decode_planar<<<(unsigned)warps, 32, sizeof(DecodeSmem), st>>>(cfg);
+      ZB_LAUNCHED();
+    }
   }
   {
     const uint32_t tiles_per_chunk = (uint32_t)((chunk + kMergeTile - 1) / kMergeTile);
@@ -313,6 +459,143 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     });
     if (rc) return rc;
   }
+  if (cfg.ovf_slots) {
+    ScopedTimer tm(kKDecodeOverflow, st);
+    int rc = dispatch_G(G, [&](auto g) -> int {
+      k_decode_overflow<decltype(g)::value><<<cfg.ovf_slots, kMergeThreads, sizeof(DecodeSmem), st>>>(cfg, (uint8_t*)d_out);
+      ZB_LAUNCHED();
+      return ZIPNN_B200_OK;
+    });
+    if (rc) return rc;
+  }
+  if (check) return read_ctrl_error(d_ws, st);
+  return ZIPNN_B200_OK;
+}
+
+// ---- batches: every small/medium tensor of a checkpoint shard in ONE launch per kernel ------------------
+// Workspace: [256 B: error word][DecodeCfg n][chunk_start n+1][item_start n+1][tile_start n+1][per-tensor slices]
+static size_t batch_header_bytes(int n) {
+  return round_up(256 + sizeof(DecodeCfg) * (size_t)n + 3 * sizeof(uint64_t) * ((size_t)n + 1), 256);
+}
+static size_t batch_slice_bytes(const zipnn_b200_batch_item& it) {
+  size_t w = 0;
+  if (it.orig == 0) return 0;
+  zipnn_b200_decompress_workspace_size(it.orig, it.num_buf, it.chunk, &w);
+  return round_up(w, 256);
+}
+
+int zipnn_b200_decompress_batch_workspace_size(const zipnn_b200_batch_item* items, int n, size_t* out) {
+  if (!out || n < 0 || (n && !items)) return ZIPNN_B200_E_ARG;
+  size_t total = batch_header_bytes(n);
+  for (int i = 0; i < n; i++) {
+    if (!valid_layout(items[i].num_buf, items[i].bytes_mode, items[i].chunk)) return ZIPNN_B200_E_ARG;
+    total += batch_slice_bytes(items[i]);
+  }
+  *out = total;
+  return ZIPNN_B200_OK;
+}
+
+int zipnn_b200_decompress_batch(const zipnn_b200_batch_item* items, int n, void* d_ws, size_t ws_bytes, void* cuda_stream, int check) {
+  if (n < 0 || (n && !items) || !d_ws || ((uintptr_t)d_ws & 255)) return ZIPNN_B200_E_ARG;
+  if (n == 0) return ZIPNN_B200_OK;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  uint8_t* ws = (uint8_t*)d_ws;
+  const size_t hdr = batch_header_bytes(n);
+  if (ws_bytes < hdr) return ZIPNN_B200_E_CAPACITY;
+  const uint64_t sync_max = sync_max_chunks();
+  std::vector<DecodeCfg> cfgs((size_t)n);
+  std::vector<uint64_t> starts(3 * ((size_t)n + 1), 0);
+  uint64_t* chunk_start = starts.data();
+  uint64_t* item_start = chunk_start + (n + 1);
+  uint64_t* tile_start = item_start + (n + 1);
+  size_t at = hdr;
+  std::vector<int> big;  // tensors that go through the single-tensor path on the same stream
+  uint64_t max_ovf = 0;
+  ZB_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+  for (int i = 0; i < n; i++) {
+    const zipnn_b200_batch_item& it = items[i];
+    if (!valid_layout(it.num_buf, it.bytes_mode, it.chunk)) return ZIPNN_B200_E_ARG;
+    const size_t slice = batch_slice_bytes(it);
+    if (at + slice > ws_bytes) return ZIPNN_B200_E_CAPACITY;
+    chunk_start[i + 1] = chunk_start[i];
+    item_start[i + 1] = item_start[i];
+    tile_start[i + 1] = tile_start[i];
+    memset(&cfgs[i], 0, sizeof(DecodeCfg));
+    cfgs[i].ctrl = (Ctrl*)ws;  // (never raised: an empty tensor has no kernel work)
+    if (it.orig == 0) continue;
+    if (!it.d_body || !it.d_out || ((uintptr_t)it.d_out & 15)) return ZIPNN_B200_E_ARG;
+    const uint64_t K = num_chunks(it.orig, it.chunk);
+    const bool small = K <= sync_max;
+    const int rc = fill_decode_cfg(cfgs[i], it.d_body, it.body_len, it.num_buf, it.bits_mode, it.chunk, it.orig, it.d_out, ws + at, slice, small);
+    if (rc) return rc;
+    ZB_CUDA(cudaMemsetAsync(ws + at, 0, kCtrlBytes, st));
+    if (small) {
+      chunk_start[i + 1] += K;
+      item_start[i + 1] += 4ull * it.num_buf * K;
+      tile_start[i + 1] += K * ((it.chunk + kMergeTile - 1) / kMergeTile);
+      max_ovf = std::max<uint64_t>(max_ovf, cfgs[i].ovf_slots);
+    } else {
+      big.push_back(i);
+    }
+    at += slice;
+  }
+  // descriptors to the device (pageable source: the copy is staged before the call returns)
+  uint8_t* d_cfgs = ws + 256;
+  uint8_t* d_starts = d_cfgs + sizeof(DecodeCfg) * (size_t)n;
+  ZB_CUDA(cudaMemcpyAsync(d_cfgs, cfgs.data(), sizeof(DecodeCfg) * (size_t)n, cudaMemcpyHostToDevice, st));
+  ZB_CUDA(cudaMemcpyAsync(d_starts, starts.data(), sizeof(uint64_t) * starts.size(), cudaMemcpyHostToDevice, st));
+  BatchCfg B;
+  B.cfgs = (const DecodeCfg*)d_cfgs;
+  B.chunk_start = (const uint64_t*)d_starts;
+  B.item_start = B.chunk_start + (n + 1);
+  B.tile_start = B.item_start + (n + 1);
+  B.n = (uint32_t)n;
+  B.error_out = (uint32_t*)ws;
+  const int sms = sm_count_cached();
+  if (chunk_start[n]) {
+    {
+      const int threads = 128;
+      const unsigned blocks = (unsigned)std::min<uint64_t>((chunk_start[n] + threads - 1) / threads, 4096);
+      ScopedTimer tm(kKDecodeMeta, st);
+      k_decode_meta_batch<<<blocks, threads, 0, st>>>(B);
+      ZB_LAUNCHED();
+    }
+    {
+      static bool attr_done = false;
+      if (!attr_done) {
+        ZB_CUDA(cudaFuncSetAttribute(k_huf_decode_sync_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncShared)));
+        attr_done = true;
+      }
+      static const int nb = [] {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_huf_decode_sync_batch, kSyncThreads, sizeof(SyncShared)) != cudaSuccess || v < 1) v = 1;
+        return v;
+      }();
+      const unsigned grid = (unsigned)std::min<uint64_t>(item_start[n], (uint64_t)nb * sms);
+      ScopedTimer tm(kKHufDecodeSync, st);
+      k_huf_decode_sync_batch<<<grid, kSyncThreads, sizeof(SyncShared), st>>>(B);
+      ZB_LAUNCHED();
+    }
+    {
+      const unsigned grid = (unsigned)std::min<uint64_t>(tile_start[n], (uint64_t)sms * 16);
+      ScopedTimer tm(kKRegroup, st);
+      k_regroup_batch<<<grid, kMergeThreads, 0, st>>>(B);
+      ZB_LAUNCHED();
+    }
+    if (max_ovf) {
+      ScopedTimer tm(kKDecodeOverflow, st);
+      k_decode_overflow_batch<<<dim3((unsigned)max_ovf, (unsigned)n), kMergeThreads, sizeof(DecodeSmem), st>>>(B);
+      ZB_LAUNCHED();
+    }
+  }
+  for (int i : big) {
+    const zipnn_b200_batch_item& it = items[i];
+    const int rc = zipnn_b200_decompress(it.d_body, it.body_len, it.num_buf, it.bits_mode, it.bytes_mode, it.chunk, it.orig, it.d_out,
+                                         (void*)cfgs[i].ctrl, batch_slice_bytes(it), st, 0);
+    if (rc) return rc;
+  }
+  k_batch_errors<<<1, 256, 0, st>>>(B);
+  ZB_LAUNCHED();
   if (check) return read_ctrl_error(d_ws, st);
   return ZIPNN_B200_OK;
 }

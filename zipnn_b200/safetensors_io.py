@@ -52,8 +52,12 @@ class SafeOpen:
     """`safetensors.safe_open` wrapper that decodes compressed tensors on access
     (zipnn/zipnn.py:1592-1626)."""
 
-    def __init__(self, filename, framework, device="cpu"):
+    def __init__(self, filename, framework, device="cpu", batch=True):
+        """`batch` (CUDA devices only): decode all compressed tensors of the file with one batched call on
+        the first access instead of one call per tensor; costs device memory for the whole file at once."""
         self._device = device
+        self._batch = batch
+        self._ready = {}
         self._filename = filename
         self._f = _safe_open(filename, framework, device)
         self.compressed_tensors_metadata = get_compressed_tensors_metadata(self._f.metadata())
@@ -74,6 +78,15 @@ class SafeOpen:
             self._index = _safetensors_index(self._filename)
             self._fd = os.open(self._filename, os.O_RDONLY)
             self._pipe = DecodePipe(self._cuda)
+            if self._batch:
+                # every compressed entry of the file in one go: one read of the byte range, one H2D buffer,
+                # ONE launch per decode kernel for the whole shard; tensors are handed out as they are asked for
+                names = sorted(self.compressed_tensors_metadata, key=lambda k: self._index[k][0])
+                names = [k for k in names if k in self._index]
+                got = self._pipe.submit_file_batch(self._fd, [self._index[k] for k in names])
+                self._ready = {k: t for k, t in zip(names, got) if t is not None}
+        if name in self._ready:
+            return self._ready.pop(name)
         off, nbytes = self._index[name]
         znn = ZipNN(input_format="torch", bytearray_dtype=COMPRESSED_DTYPE, method=COMPRESSION_METHOD)
         return self._pipe.submit_file(self._fd, off, nbytes, znn)
@@ -82,6 +95,7 @@ class SafeOpen:
         """Wait for the decodes still in flight and raise what they found (corrupt stream, ...)."""
         pipe, self._pipe = self._pipe, None
         fd, self._fd = self._fd, None
+        self._ready = {}
         try:
             if pipe is not None:
                 pipe.finish()
