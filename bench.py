@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-sample-gib", type=float, default=1.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
     return ap.parse_args()
 
 
@@ -118,8 +119,9 @@ def make_tensor(nbytes, dtype, device, seed):
     return out
 
 
-def cpu_reference_codec():
-    """-> (kind, compress(bytes, threads) -> stream, decompress(stream, n, threads), release(buffer))."""
+def cpu_reference_codec(num_buf=2, bits=1, bytes_mode=10, chunk=262144):
+    """-> (kind, compress(bytes, threads) -> stream, decompress(stream, n, threads), release(buffer)).
+    Layout defaults = bf16 (zipnn/zipnn.py:803-808); fp16 (2,0,10), fp32 (4,1,220), fp8 (1,1,10, chunk 131072)."""
     from oracle import oracle as O
     ref = O.ref_core()
     hdr = bytearray(32)
@@ -132,10 +134,10 @@ def cpu_reference_codec():
         libc_free.restype = None
 
         def comp(buf, th):
-            return ref.zipnn_core(bytes(hdr), buf, 2, 1, 10, 0, 262144, 0.95, 10, th)
+            return ref.zipnn_core(bytes(hdr), buf, num_buf, bits, bytes_mode, 0, chunk, 0.95, 10, th)
 
         def dec(stream, n, th):
-            return ref.combine_dtype(memoryview(stream)[32:], 2, 1, 10, 262144, n, th)
+            return ref.combine_dtype(memoryview(stream)[32:], num_buf, bits, bytes_mode, chunk, n, th)
 
         def release(mv):
             # the reference wraps a malloc'ed buffer in an owner-less memoryview (csrc/zipnn_core.c:122,594-595,
@@ -152,10 +154,10 @@ def cpu_reference_codec():
     import numpy as np
 
     def comp(buf, th):
-        return O.zipnn_compress(hdr, np.frombuffer(buf, dtype=np.uint8), 2, 1, 10, 262144, 0.95, threads=th)
+        return O.zipnn_compress(hdr, np.frombuffer(buf, dtype=np.uint8), num_buf, bits, bytes_mode, chunk, 0.95, threads=th)
 
     def dec(stream, n, th):
-        return O.zipnn_decompress(np.asarray(stream)[32:], 2, 1, 10, 262144, n, threads=th)
+        return O.zipnn_decompress(np.asarray(stream)[32:], num_buf, bits, bytes_mode, chunk, n, threads=th)
     return "port", comp, dec, (lambda mv: None)
 
 
@@ -292,12 +294,132 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and the threads / pinned buffers it creates afterwards) to the CPUs that share a
+    NUMA node with its GPU: 8 ranks that all stage through node 0's memory halve each other's PCIe rate."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        cpus = [c for c in cpus if c < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"bound": True, "cpus": f"{min(cpus)}-{max(cpus)} ({len(cpus)})"}
+            try:
+                for node in sorted(os.listdir("/sys/devices/system/node")):
+                    if node.startswith("node") and os.path.exists(f"/sys/devices/system/node/{node}/cpu{cpus[0]}"):
+                        info["numa_node"] = int(node[4:])
+            except Exception:
+                pass
+    except Exception as exc:  # no NVML / not permitted: run unbound and say so
+        info["error"] = str(exc)[:120]
+    return info
+
+
+def run_sharded(args, rank, world, dev, total_bytes, dtype):
+    """ONE tensor of `total_bytes`, chunk ranges partitioned over the ranks (zipnn_b200.sharded): local codec
+    with no communication, then the per-rank payloads gathered into rank 0's buffer with point-to-point
+    NCCL sends (NVLink), giving the byte-identical single-GPU stream; the way back scatters payload ranges.
+    Codec time and exchange time are reported separately."""
+    import torch
+    import torch.distributed as dist
+    from zipnn_b200 import ZipNN
+    from zipnn_b200.sharded import HEADER_LEN, ShardedZipNN, byte_range, gather_stream
+    from zipnn_b200.util_torch import zipnn_pack_shape
+    esz = torch.empty(0, dtype=dtype).element_size()
+    n_elems = total_bytes // esz
+    chunk = 131072 if esz == 1 else 262144
+    b0, b1 = byte_range(n_elems * esz, chunk, rank, world)
+    # every rank draws the same stream of random numbers, slab by slab, and keeps its own byte range
+    g = torch.Generator(device=dev).manual_seed(4321)
+    local = torch.empty((b1 - b0) // esz, dtype=dtype, device=dev)
+    full = torch.empty(n_elems, dtype=dtype, device=dev) if rank == 0 else None
+    slab = 1 << 27
+    for i in range(0, n_elems, slab):
+        m = min(slab, n_elems - i)
+        piece = (torch.randn(m, generator=g, device=dev, dtype=torch.float32) * (0.5 if esz == 1 else 0.02)).to(dtype)
+        lo, hi = max(i, b0 // esz), min(i + m, b1 // esz)
+        if hi > lo:
+            local[lo - b0 // esz: hi - b0 // esz] = piece[lo - i: hi - i]
+        if full is not None:
+            full[i: i + m] = piece
+        del piece
+    z = ShardedZipNN()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    res = {}
+    reps = 3
+    tc, tg, ts, td = [], [], [], []
+    stream = None
+    for it in range(reps + 1):
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        lstream, plan = z.compress_local(local)
+        e1.record()
+        n_local = local.numel() * esz
+        K_local = (n_local + plan["chunk"] - 1) // plan["chunk"]
+        gh = bytes(bytearray(plan["header"][:HEADER_LEN])) + zipnn_pack_shape((n_elems,))
+        stream = gather_stream(lstream, HEADER_LEN, plan["num_buf"], K_local, n_local, gh, 0, None, chunk=plan["chunk"])
+        e2.record()
+        torch.cuda.synchronize(); dist.barrier()
+        e3, e4 = ev(), ev()
+        e3.record()
+        back = z.decompress(stream if rank == 0 else None, src=0, device=dev)
+        e4.record()
+        torch.cuda.synchronize()
+        if it:
+            tc.append(e0.elapsed_time(e1)); tg.append(e1.elapsed_time(e2)); td.append(e3.elapsed_time(e4))
+        if it == 0:
+            ok_local = bool(torch.equal(back.view(torch.uint8), local.view(torch.uint8)))
+        if it < reps:
+            del lstream, back
+            if rank != 0:
+                stream = None
+    vals = torch.tensor([sum(tc) / reps, sum(tg) / reps, sum(td) / reps, 0.0 if ok_local else 1.0], device=dev, dtype=torch.float64)
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    codec_ms, gather_ms, dec_total_ms, bad = [float(x) for x in vals.tolist()]
+    if rank == 0:
+        want = ZipNN(input_format="torch").compress(full)
+        same = stream.numel() == want.numel() and bool(torch.equal(stream, want))
+        # decompress side: local decode time of rank 0's shard alone, to split scatter from codec
+        own = ShardedZipNN()
+        ls0, _ = own.compress_local(local)
+        a, b = ev(), ev()
+        a.record()
+        own._codec()[1](ls0[HEADER_LEN:], plan["num_buf"], plan["bit_reorder"], plan["byte_reorder"], plan["chunk"], local.numel() * esz)
+        b.record()
+        torch.cuda.synchronize()
+        dec_codec_ms = a.elapsed_time(b)
+        C = int(stream.numel())
+        moved = C * (world - 1) // world
+        N = n_elems * esz
+        res = {"tensor_bytes": N, "stream_bytes": C, "ranks": world, "stream_equals_single_gpu": bool(same), "round_trip_exact": bad == 0.0,
+               "compress": {"codec_ms": round(codec_ms, 3), "gather_ms": round(gather_ms, 3), "nvlink_bytes_into_owner": moved,
+                            "gather_gbs_into_owner": round(moved / (gather_ms * 1e-3) / 1e9, 1) if gather_ms > 0 else None,
+                            "gbs_of_N": round(N / ((codec_ms + gather_ms) * 1e-3) / 1e9, 1), "codec_only_gbs_of_N": round(N / (codec_ms * 1e-3) / 1e9, 1)},
+               "decompress": {"scatter_plus_codec_ms": round(dec_total_ms, 3), "codec_ms_rank0": round(dec_codec_ms, 3),
+                              "scatter_ms_estimate": round(max(dec_total_ms - dec_codec_ms, 0.0), 3),
+                              "gbs_of_N": round(N / (dec_total_ms * 1e-3) / 1e9, 1)},
+               "limiter": "the exchange: C*(R-1)/R bytes enter / leave ONE GPU over its NVLink ports (~0.75 TB/s measured peer rate), while the codec side scales with R",
+               "note": "the reference has no distributed path; this is the design BASELINE.json's north_star describes (chunks partition, NCCL only gathers the stream)"}
+        del want, full
+    del local, stream
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from zipnn_b200 import ZipNN, _native
 
+    numa = bind_to_gpu_numa(local_rank) if world > 1 or os.environ.get("ZIPNN_BENCH_BIND") else {"bound": False}
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -388,7 +510,17 @@ def run_ours(args, rank, local_rank, world):
         e2e = {"value": round(world * eb / (e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": world * (eb + c_e2e),
                "d2h_bytes_per_step": world * (c_e2e + eb), "ms_per_step": round(e_ms, 2), "bytes_per_gpu": eb,
                "api": "zipnn_b200.ZipNN(input_format='torch').compress(pinned cpu tensor, out=pinned) / .decompress(host stream, out=pinned): H2D copy, zipnn_b200_compress / _decompress, D2H copy"}
-        del ht
+        e2e["numa"] = numa
+        # per-rank one-way PCIe rates of the e2e region (the limiter at 8 GPUs is host memory / root ports, not the codec)
+        del ht, hs_buf, hd_buf
+
+    # ---- the sharded path (N > 1): one tensor partitioned by chunk range, NCCL gathers / scatters the stream
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        del t                      # (the CPU leg below runs at N = 1 only)
+        t = None
+        torch.cuda.empty_cache()
+        sharded = run_sharded(args, rank, world, dev, nbytes, dtype)
 
     # ---- CPU baseline beside it (rank 0, single-GPU runs only) + stream == reference stream at the bench scale
     cpu = None
@@ -466,7 +598,8 @@ def run_ours(args, rank, local_rank, world):
     per_launch = {k: (ms / max(cnt, 1), cnt) for k, (ms, cnt) in ktimes.items() if cnt}
     dom = max(per_launch, key=lambda k: per_launch[k][0] * per_launch[k][1])
     N, Cb = nbytes, stream_bytes
-    G = 1 if t.element_size() == 1 else (2 if t.element_size() == 2 else 4)
+    esz_t = torch.empty(0, dtype=dtype).element_size()
+    G = 1 if esz_t == 1 else (2 if esz_t == 2 else 4)
     huf_payload = Cb - (N // G) * (G - 1) if G > 1 else Cb  # bytes of the Huffman-coded group(s) (the others are stored raw)
     algo = {  # algorithmic bytes per launch, see DESIGN.md "kernels"
         "k_encode_hist": N,                     # reads every input byte once
@@ -512,6 +645,8 @@ def run_ours(args, rank, local_rank, world):
         line["cpu_baseline"] = cpu
     if parity:
         line["parity_check"] = parity
+    if sharded:
+        line["sharded"] = sharded
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

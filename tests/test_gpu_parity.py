@@ -271,6 +271,18 @@ def test_streaming_and_delta_frames():
     s = zd.compress(base, delta_second_data=a)
     out = ZipNN(input_format="byte", bytearray_dtype="bfloat16", delta_compressed_type="byte").decompress(bytes(s), delta_second_data=a)
     assert bytes(out) == base
+    # the delta stream is the reference's: XOR on the host, then the plain codec (zipnn/zipnn.py:636-640)
+    x = np.bitwise_xor(np.frombuffer(base, dtype=np.uint8), np.frombuffer(a, dtype=np.uint8))
+    plan = ZipNN(input_format="byte", bytearray_dtype="bfloat16", delta_compressed_type="byte").plan(x.tobytes())
+    want = O.zipnn_compress(plan["header"], x, 2, 1, 10, 262144, 0.95, threads=4)
+    assert bytes(s) == want.tobytes()
+    # device-resident operands: the XOR runs on the GPU and CUDA tensors come back
+    d_base = torch.frombuffer(bytearray(base), dtype=torch.uint8).cuda()
+    d_a = torch.frombuffer(bytearray(a), dtype=torch.uint8).cuda()
+    sd = ZipNN(input_format="byte", bytearray_dtype="bfloat16", delta_compressed_type="byte").compress(d_base, delta_second_data=d_a)
+    assert sd.is_cuda and sd.cpu().numpy().tobytes() == want.tobytes()
+    od = ZipNN(input_format="byte", bytearray_dtype="bfloat16", delta_compressed_type="byte").decompress(sd, delta_second_data=d_a)
+    assert od.is_cuda and od.cpu().numpy().tobytes() == base
 
 
 # ------------------------------------------------------------------ size-independent properties at scale
@@ -305,10 +317,9 @@ def test_large_round_trip_properties():
 
 
 def test_pipelined_host_decompress(monkeypatch):
-    """Host streams above a size threshold are decoded slab by slab on two CUDA streams."""
-    import zipnn_b200.zipnn as zz
-    monkeypatch.setattr(zz, "PIPELINE_MIN_BYTES", 1 << 20)
-    monkeypatch.setattr(zz, "PIPELINE_SLAB_BYTES", 3 * 262144)
+    """Host streams above a size threshold are decoded slab by slab on two CUDA streams, inside
+    zipnn_b200_decompress_host (the environment knob shrinks the slabs so small inputs take that path)."""
+    monkeypatch.setenv("ZIPNN_B200_HOST_SLAB_BYTES", str(3 * 262144))
     g = torch.Generator().manual_seed(5)
     for dt, n in ((torch.bfloat16, 5 * 131072 * 2 + 12345), (torch.float32, 11 * 65536 + 7), (torch.float8_e4m3fn, 9 * 131072 + 1)):
         t = (torch.randn(n, generator=g) * 0.02).to(dt)
@@ -325,9 +336,8 @@ def test_pipelined_host_decompress(monkeypatch):
 
 @pytest.mark.gpu
 def test_pipelined_host_compress(monkeypatch):
-    """Large host inputs are compressed slab by slab (H2D of the next slab, D2H of group 0 of the
-    previous one in flight together); the stream must equal the one-shot device stream byte for byte."""
-    import zipnn_b200.zipnn as zz
+    """Large host inputs are compressed slab by slab inside zipnn_b200_compress_host (H2D of the next slab, D2H
+    of group 0 of the previous one in flight together); the stream must equal the one-shot device stream."""
     g = torch.Generator().manual_seed(7)
     cases = ((torch.bfloat16, 5 * 131072 * 2 + 12345), (torch.float32, 11 * 65536 + 7), (torch.float16, 7 * 131072),
              (torch.float8_e4m3fn, 9 * 131072 + 1))
@@ -336,14 +346,65 @@ def test_pipelined_host_compress(monkeypatch):
         t[1000:200000] = 0  # RLE planes in some chunks
         one_shot = ZipNN(input_format="torch").compress(t.cuda()).cpu().numpy().tobytes()
         with monkeypatch.context() as m:
-            m.setattr(zz, "PIPELINE_MIN_BYTES", 1 << 20)
-            m.setattr(zz, "PIPELINE_SLAB_BYTES", 3 * 262144)
+            m.setenv("ZIPNN_B200_HOST_SLAB_BYTES", str(3 * 262144))
             piped = bytes(ZipNN(input_format="torch").compress(t))
             out = torch.empty(len(one_shot) + 4096, dtype=torch.uint8, pin_memory=True)
             piped_out = bytes(ZipNN(input_format="torch").compress(t.pin_memory(), out=out))
         assert piped == one_shot and piped_out == one_shot, str(dt)
         back = ZipNN(input_format="torch").decompress(piped)
         assert raw_bytes(back) == raw_bytes(t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slab", [None, 3 * 262144])
+def test_host_exports_with_plain_malloc_buffers(slab, monkeypatch):
+    """zipnn_b200_compress_host / zipnn_b200_decompress_host called the way a C extension standing in for the
+    reference's zipnn_core module would (csrc/zipnn_core.c:401-417, 881-892): pageable malloc'ed host buffers,
+    no torch in between.  Stream == oracle stream; round trip exact; also a mixed case where a later group is
+    coded although the first is raw (the early-copy bet of the slab path is lost and repaired)."""
+    if slab:
+        monkeypatch.setenv("ZIPNN_B200_HOST_SLAB_BYTES", str(slab))
+    L = _native.lib()
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(31)
+    cases = []
+    x = (rng.standard_normal(131072 * 7 + 333) * 0.02).astype(np.float32)
+    cases.append((2, 1, 10, 262144, np.ascontiguousarray((x.view(np.uint32) >> 16).astype(np.uint16).view(np.uint8))))    # bf16
+    cases.append((4, 1, 220, 262144, np.ascontiguousarray(x.view(np.uint8)[: 65536 * 4 * 5 + 8])))                          # fp32
+    cases.append((1, 0, 10, 131072, rng.choice(6, 131072 * 5 + 1, p=[.5, .25, .12, .06, .04, .03]).astype(np.uint8)))       # fp8-like, all coded
+    mixed = np.ascontiguousarray((x.view(np.uint32) >> 16).astype(np.uint16).view(np.uint8)).copy()
+    mixed[0: 262144 * 2: 2] = 7           # the low byte plane of two chunks becomes compressible: group 0 is no longer all raw
+    cases.append((2, 1, 10, 262144, mixed))
+    for G, bits, bm, chunk, data in cases:
+        n = data.size
+        hdr = bytearray(32)
+        hdr[0:2] = b"ZN"
+        want = O.zipnn_compress(hdr, data, G, bits, bm, chunk, 0.95, threads=4)
+        bound = _native.compress_bound(n, G, chunk, 32)
+        p_in, p_out, p_back = libc.malloc(n), libc.malloc(bound), libc.malloc(n)
+        try:
+            C.memmove(p_in, data.ctypes.data, n)
+            out_len = C.c_size_t(0)
+            hbuf = (C.c_char * 32).from_buffer_copy(bytes(hdr))
+            rc = L.zipnn_b200_compress_host(p_in, n, hbuf, 32, G, bits, bm, chunk, 0.95, p_out, bound, C.byref(out_len))
+            assert rc == 0
+            got = np.frombuffer((C.c_char * out_len.value).from_address(p_out), dtype=np.uint8)
+            assert out_len.value == want.size and np.array_equal(got, want), (G, bits, n)
+            rc = L.zipnn_b200_decompress_host(p_out + 32, out_len.value - 32, G, bits, bm, chunk, n, p_back)
+            assert rc == 0
+            back = np.frombuffer((C.c_char * n).from_address(p_back), dtype=np.uint8)
+            assert np.array_equal(back, data)
+            # a corrupt type byte is reported, not decoded
+            bad = np.array(got, copy=True)
+            bad[32 + 1 if G * ((n + chunk - 1) // chunk) > 1 else 32] = 5
+            C.memmove(p_out, bad.ctypes.data, bad.size)
+            assert L.zipnn_b200_decompress_host(p_out + 32, out_len.value - 32, G, bits, bm, chunk, n, p_back) == _native.E_CORRUPT
+        finally:
+            for q in (p_in, p_out, p_back):
+                libc.free(q)
 
 
 # ------------------------------------------------------------------ round-2 paths

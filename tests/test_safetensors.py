@@ -190,3 +190,38 @@ def test_tensor_with_many_general_chunks_is_correct_inside_the_with_block(tmp_pa
             torch.cuda.current_stream().synchronize()
             assert torch.equal(got_big.cpu(), big), f"batch={batch}"
             assert torch.equal(got_small.cpu(), small)
+
+
+@pytest.mark.gpu
+def test_zipnn_hf_loads_znn_checkpoints(tmp_path):
+    """zipnn_hf(): transformers' load_state_dict reads `model.safetensors.znn` (the reference's whole-file
+    streaming format), and from_pretrained on a directory that only holds the .znn file finds the weights."""
+    import transformers
+    from transformers import GPT2Config, GPT2LMHeadModel, modeling_utils
+    from zipnn_b200 import ZipNN, zipnn_hf
+    cfg = GPT2Config(n_layer=2, n_head=2, n_embd=64, vocab_size=257, n_positions=32)
+    torch.manual_seed(0)
+    model = GPT2LMHeadModel(cfg)
+    d = tmp_path / "ckpt"
+    model.save_pretrained(str(d), safe_serialization=True)
+    plain = d / "model.safetensors"
+    raw = plain.read_bytes()
+    znn = ZipNN(input_format="byte", bytearray_dtype="float32", is_streaming=True).compress(raw)
+    # the whole-file stream is the reference's: frame 0 == the oracle's stream of the first MiB
+    from oracle import oracle as O
+    import numpy as np
+    first = raw[: 1 << 20]
+    plan = ZipNN(input_format="byte", bytearray_dtype="float32", is_streaming=True).plan(first)
+    want = O.zipnn_compress(plan["header"], np.frombuffer(first, dtype=np.uint8), 4, 1, 220, 262144, 0.95, threads=2)
+    assert bytes(znn[: want.size]) == want.tobytes()
+    (d / "model.safetensors.znn").write_bytes(bytes(znn))
+    plain.unlink()
+    zipnn_hf()
+    sd = modeling_utils.load_state_dict(str(d / "model.safetensors.znn"))
+    ref = model.state_dict()
+    assert set(sd) <= set(ref) and all(torch.equal(sd[k].cpu(), ref[k]) for k in sd)
+    again = GPT2LMHeadModel.from_pretrained(str(d))
+    for k, v in again.state_dict().items():
+        assert torch.equal(v, ref[k]), k
+    assert (d / "model.safetensors.znn").exists() and not plain.exists()   # replace_local_file defaults to False
+    _ = transformers

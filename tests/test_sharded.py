@@ -101,3 +101,41 @@ def test_chunk_ranges_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == K
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
     assert byte_range(1000, 256, 1, 2) == (512, 1000)
+
+
+def _misaligned_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from zipnn_b200.sharded import ShardedZipNN
+        comp, dec = _oracle_codecs()
+        g = torch.Generator().manual_seed(3)
+        # an "even split" that is not chunk aligned: rank 0 holds 1.5 chunks
+        local = (torch.randn(196608 if rank == 0 else 65536, generator=g) * 0.02).to(torch.bfloat16)
+        z = ShardedZipNN(compress_local=comp, decompress_local=dec)
+        try:
+            z.compress(local, global_shape=(196608 + 65536,), dst=0)
+            q.put((rank, "no error"))
+        except ValueError as e:
+            q.put((rank, "ok" if "whole number" in str(e) else "wrong message " + str(e)))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_misaligned_shards_are_refused():
+    """a shard that is not a whole number of chunks would yield a stream with a short chunk in
+    the middle, silently different from the single-GPU stream."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_misaligned_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

@@ -4,10 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import make_tensor
 from zipnn_b200 import ZipNN
-import zipnn_b200.zipnn as _zz
 
-if os.environ.get("ZIPNN_SLAB_MIB"):      # experiment knob: slab size of the host pipelines
-    _zz.PIPELINE_SLAB_BYTES = int(os.environ["ZIPNN_SLAB_MIB"]) << 20
+if os.environ.get("ZIPNN_SLAB_MIB"):      # experiment knob: slab size of the host pipelines (read by the library)
+    os.environ["ZIPNN_B200_HOST_SLAB_BYTES"] = str(int(os.environ["ZIPNN_SLAB_MIB"]) << 20)
 
 gib = float(sys.argv[1]) if len(sys.argv) > 1 else 8.0
 n = int(gib * (1 << 30))

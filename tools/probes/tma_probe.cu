@@ -79,13 +79,14 @@ static int check_load(EncodeFn enc, uint8_t* d_buf, const std::vector<uint8_t>& 
   uint8_t* d_dst;
   cudaMalloc(&d_dst, 32 * inner);
   int bad_total = 0;
-  const uint32_t xs[3] = {(uint32_t)r0, (uint32_t)(r0 + (seg / 2 / inner) * inner), (uint32_t)(r0 + seg - inner)};  // first, middle, LAST tile of a segment
+  const uint32_t xs[3] = {(uint32_t)r0, (uint32_t)(r0 + (seg / 2 / 16) * 16), (uint32_t)(r0 + seg - inner + (overlap ? 16 : 0))};  // first, middle, LAST tile of a segment
   for (int t = 0; t < 3; t++) {
     const uint32_t y0 = 32;
     cudaMemset(d_dst, 0xEE, 32 * inner);
     if (inner == 16) k_load<16><<<1, 32>>>(m, xs[t], y0, d_dst);
     if (inner == 32) k_load<32><<<1, 32>>>(m, xs[t], y0, d_dst);
     if (inner == 64) k_load<64><<<1, 32>>>(m, xs[t], y0, d_dst);
+    if (inner == 48) k_load<48><<<1, 32>>>(m, xs[t], y0, d_dst);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("  kernel error %s\n", cudaGetErrorString(e)); return 1; }
     std::vector<uint8_t> got(32 * inner);
@@ -128,9 +129,10 @@ int main(int argc, char** argv) {
     case 1: fails = check_load(enc, d, h, 1029, seg, rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE, "T1 unaligned x, 16B, no swizzle", false); break;
     case 2: fails = check_load(enc, d, h, 77, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_32B, "T2 unaligned x, 32B, swizzle32", false); break;
     case 3: fails = check_load(enc, d, h, 77, seg, rows, 64, CU_TENSOR_MAP_SWIZZLE_64B, "T3 unaligned x, 64B, swizzle64", false); break;
-    case 4: fails = check_load(enc, d, h, 1029, seg, rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE, "T4 overlap rows, 16B", true); break;
-    case 5: fails = check_load(enc, d, h, 77, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_32B, "T5 overlap rows, 32B swizzle32", true); break;
-    case 6: fails = check_load(enc, d, h, 77, seg, rows, 64, CU_TENSOR_MAP_SWIZZLE_64B, "T6 overlap rows, 64B swizzle64", true); break;
+    case 4: fails = check_load(enc, d, h, 1024, seg, rows, 16, CU_TENSOR_MAP_SWIZZLE_NONE, "T4 overlap rows, 16B, aligned x", true); break;
+    case 5: fails = check_load(enc, d, h, 64, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_32B, "T5 overlap rows, 32B swizzle32, aligned x", true); break;
+    case 6: fails = check_load(enc, d, h, 64, seg, rows, 64, CU_TENSOR_MAP_SWIZZLE_64B, "T6 overlap rows, 64B swizzle64, aligned x", true); break;
+    case 9: fails = check_load(enc, d, h, 64, seg, rows, 48, CU_TENSOR_MAP_SWIZZLE_NONE, "T9 overlap rows, 48B rows, last tile spills 16 B into the next row", true); break;
     case 7: fails = check_load(enc, d, h, 0, seg, rows, 32, CU_TENSOR_MAP_SWIZZLE_NONE, "T7 aligned, 32B, no swizzle", false); break;
     case 8: {
       const uint64_t rowb = 65536, nrows = 64;

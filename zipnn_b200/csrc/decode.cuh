@@ -18,8 +18,17 @@
 #include <cuda.h>
 #include "common.cuh"
 
+// L2 fetch granularity of the 16-byte cp.async copies that feed the bitstream rings and the side-plane slots.
+// Every lane walks its own stream, 16 bytes at a time, so the DRAM sees hundreds of thousands of interleaved
+// sequential streams; with plain sector fills each miss opens a DRAM row for 32 bytes.
+#ifndef ZB_CPASYNC_L2
+#define ZB_CPASYNC_L2 ".L2::128B"
+#endif
+
 #ifndef ZB_SIDE_SLOTS
-#define ZB_SIDE_SLOTS 2  // 16-byte cp.async slots per lane and side plane of the fused kernel (2 or 4)
+#define ZB_SIDE_SLOTS 4  // 16-byte cp.async slots per lane and side plane of the fused kernel.  2 would do (block k+3 is
+                         // requested two iterations before it is read) and saves 1 KiB per plane, but a cp.async into a slot
+                         // that an LDS read an instant earlier is slow on B200: 9.65 ms instead of 8.52 (profiles/r2_decode_probe.txt)
 #endif
 
 namespace zb {
@@ -257,7 +266,7 @@ static_assert(32 * kRingBytes >= kDecItemsPerWarp * 256, "weights alias the ring
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global" ZB_CPASYNC_L2 " [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -411,7 +420,9 @@ struct LutCol {
   __device__ __forceinline__ int32_t get(uint32_t x) const {
     const uint32_t idx = x & 0x7FFu;
     int32_t e = lds_s16((x & 0x7C0u) | col_s);
+#ifndef ZB_EXP_NOTAIL   // timing experiment only (wrong symbols for long codes)
     if (idx < x_long) e = lds_s16(tail_s + idx + idx);
+#endif
     return e;
   }
 };
@@ -775,25 +786,28 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   ring  [32][64]         2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
 //   stage [32][128]        4 KiB   one 128-byte output row per lane (1 KiB aligned, 16-byte units XOR-
 //                                  swizzled by the row); the tANS scratch of the parse aliases it
-//   side                           TMA: 2 stages x (G-1) tiles of [32][16*T]; cp.async path: (G-1) x 1 KiB
-//                                  of slots (2 per lane).  The two uses alias.
-// bf16: 2 + 1 + 2 + 2 + 4 + 1 = 12 KiB -> 17 warps per SM;  fp32: 13 KiB -> 16.
+//   side                           cp.async path: (G-1) x 2 KiB of slots (4 x 16 bytes per lane and plane);
+//                                  bulk-tensor path (16-bit types): 2 stages x [32 lanes][48 bytes] = 3 KiB.
+//                                  The two uses alias.
+// bf16: 2 + 1 + 2 + 2 + 4 + 3 = 14 KiB -> 15 warps per SM;  fp32: 3 + 2 + 2 + 4 + 6 = 17 KiB -> 12.
 template <int G>
 struct FusedGeom {
   static constexpr int kIters = 8 / G;                 // iterations (16 symbols) per 128-byte output row
-  static constexpr int kTileIters = (G == 2) ? 2 : 1;  // iterations covered by one side tile
-  static constexpr int kTilesPerRow = kIters / kTileIters;
-  static constexpr uint32_t kTileBytes = 32u * 16u * kTileIters;  // one plane, one stage
   static constexpr int NS = (G > 1) ? G - 1 : 1;
-  static constexpr uint32_t kSlotBytes = 512u * ZB_SIDE_SLOTS;                       // one side plane's cp.async slots (32 lanes)
-  static constexpr uint32_t kSideExtra = (G == 1) ? 0u : (uint32_t)(G - 1) * kSlotBytes - (ZB_SIDE_SLOTS == 2 ? 1024u : 0u);  // PB = 5: beyond the 1 KiB gap
-  static constexpr uint32_t kSideAll = (G == 1) ? 0u : (uint32_t)(G - 1) * kSlotBytes;    // PB = 0: everything
+  static constexpr uint32_t kSlotBytes = 512u * ZB_SIDE_SLOTS;   // one side plane's cp.async slots (32 lanes)
+  // Bulk-tensor side tiles (16-bit types): one tile serves two iterations: [32 lanes][32 bytes + 16], because a box
+  // must start on a 16-byte boundary of global memory and the raw plane sits at any byte offset inside the stream.
+  static constexpr int kTileIters = 2;
+  static constexpr uint32_t kTileRow = 16u * kTileIters + 16u, kTileBytes = 32u * kTileRow;
+  static constexpr uint32_t kTileRegion = (G == 2) ? 2u * kTileBytes : 0u;
+  static constexpr uint32_t kSlotRegion = (G == 1) ? 0u : (uint32_t)(G - 1) * kSlotBytes;
+  static constexpr uint32_t kSideAll = kSlotRegion > kTileRegion ? kSlotRegion : kTileRegion;
 };
 __host__ __device__ constexpr uint32_t fused_tail_bytes(int pb) { return pb == 0 ? 4096u : 2048u; }
 __host__ __device__ constexpr uint32_t fused_tail_cap(int pb) { return (fused_tail_bytes(pb) - 16u) / 2u; }  // entries (multiple of 8)
 template <int G>
 __host__ __device__ constexpr size_t fused_smem_bytes(int pb) {
-  return (pb == 0 ? (size_t)4096 + FusedGeom<G>::kSideAll : (size_t)3072 + FusedGeom<G>::kSideExtra) + fused_tail_bytes(pb) + 32 * kRingBytes + 32 * 128;
+  return (pb == 0 ? (size_t)4096 : (size_t)3072) + FusedGeom<G>::kSideAll + fused_tail_bytes(pb) + 32 * kRingBytes + 32 * 128;
 }
 struct FusedSmem {
   unsigned char* raw;
@@ -834,21 +848,11 @@ __device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw) {
   S.side_off = at;
   return S;
 }
-// Shared address of side tile (stage st, plane g) / of plane g's cp.async slots.
-template <int G, int PB>
-__device__ __forceinline__ uint32_t side_tile_s(const FusedSmem& S, int st, int g) {
-  using Geo = FusedGeom<G>;
-  const uint32_t idx = (uint32_t)(st * (G - 1) + g);
-  if (PB == 0) return S.base_s + S.side_off + idx * Geo::kTileBytes;
-  constexpr uint32_t in_gap = 1024u / Geo::kTileBytes;
-  return idx < in_gap ? S.base_s + S.gap_off + idx * Geo::kTileBytes : S.base_s + S.side_off + (idx - in_gap) * Geo::kTileBytes;
-}
-template <int G, int PB>
-__device__ __forceinline__ uint32_t side_slots_s(const FusedSmem& S, int g) {
-  constexpr uint32_t sb = FusedGeom<G>::kSlotBytes;
-  if (PB == 0 || ZB_SIDE_SLOTS != 2) return S.base_s + S.side_off + (uint32_t)g * sb;
-  return g == 0 ? S.base_s + S.gap_off : S.base_s + S.side_off + (uint32_t)(g - 1) * sb;   // two slots: plane 0 fits the 1 KiB gap
-}
+// Shared address of side-tile stage st / of plane g's cp.async slots (both inside the side region).
+template <int G>
+__device__ __forceinline__ uint32_t side_tile_s(const FusedSmem& S, uint32_t st) { return S.base_s + S.side_off + st * FusedGeom<G>::kTileBytes; }
+template <int G>
+__device__ __forceinline__ uint32_t side_slots_s(const FusedSmem& S, int g) { return S.base_s + S.side_off + (uint32_t)g * FusedGeom<G>::kSlotBytes; }
 static_assert(sizeof(FseDecSmall) <= 512, "small tANS scratch must fit in 4 stage rows");
 
 struct SidePlane {
@@ -868,7 +872,7 @@ struct SidePlane {
 // at the top of iteration k, joins the commit groups of the stream ring, and an LDS picks it up at
 // the end of iteration k+1, after which its slot is free for block k+5: two slots per lane and plane.
 __device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global" ZB_CPASYNC_L2 " [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
   uint4 v;
@@ -1000,6 +1004,14 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     if (lane == 0 && blockIdx.x == 0) atomicOr(&cfg.ctrl->error, kErrUnsupported);
     return;
   }
+  const uint32_t bar_s = S.base_s + S.bar_off;  // two mbarriers, one per side-tile stage
+  if (lane == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_s + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t tiles_done = 0;      // side tiles this warp has consumed: tile n sits in stage n & 1, its barrier phase is (n >> 1) & 1
   bool store_pending = false;   // a bulk store of this warp may still be reading the stage
   uint8_t (*const stage)[128] = S.stage();
   const uint32_t stage_s = S.base_s + S.stage_off;
@@ -1121,6 +1133,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     }
     regular = __all_sync(0xffffffffu, regular);
     const bool out_tma = regular && (cfg.tma_flags & kTmaOut);
+    const bool side_tma = (G == 2) && regular && (cfg.tma_flags & kTmaSide);
 
     BitWindow b;
     if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring()[lane])) {
@@ -1137,6 +1150,60 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
     }
 
     const uint32_t rows_full = (seg >> 4) / kIters;
+    if constexpr (G == 2) {
+      if (side_tma) {
+        // ================= side plane through bulk-tensor tiles (16-bit types, regular groups) =================
+        // The 32 quarter planes of this warp's 8 chunks are rows 32 * grp .. +31 of maps.side[0] (row pitch = one
+        // quarter plane).  Tile t = bytes [32 t, 32 t + 48) of every row, counted from the 16-byte boundary below
+        // the plane's first byte: the 32 bytes iterations 2t and 2t+1 pair with their symbols start side_r0 (0..15)
+        // bytes into it.  One thread asks for tile t+1 while the warp works on tile t; the bytes land in shared
+        // memory without a single LSU instruction (the cp.async path pays 32 L1 wavefronts per instruction because
+        // every lane's 16 bytes lie in a different line: a fifth of the kernel's LSU time).
+        const uint32_t y0 = (uint32_t)(grp * 32u);
+        const uint32_t ntiles = rows_full * 2u;
+        const uint32_t r0 = cfg.side_r0[0];
+        auto issue_tile = [&](uint32_t t) {
+          const uint32_t st = (tiles_done + t) & 1u;
+          mbar_expect_tx(bar_s + 8u * st, Geo::kTileBytes);
+          tma_load_2d(side_tile_s<G>(S, st), &maps.side[0], 32u * t, y0, bar_s + 8u * st);
+        };
+        if (lane == 0 && ntiles) issue_tile(0);
+        // the 8 stage rows this lane writes out each round: row r*4 + lane/8, 16-byte unit lane%8
+        const uint64_t my_out = (uint64_t)(uintptr_t)(out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G);
+        uint64_t row_out[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) row_out[r] = __shfl_sync(0xffffffffu, my_out, r * 4 + (lane >> 3)) + (uint64_t)(lane & 7) * 16;
+        for (uint32_t row = 0; row < rows_full; row++) {
+#pragma unroll
+          for (int tr = 0; tr < 2; tr++) {
+            const uint32_t t = row * 2u + (uint32_t)tr;
+            const uint32_t n = tiles_done + t;
+            __syncwarp();  // every lane has read tile t-1: its stage may be overwritten by tile t+1
+            if (lane == 0 && t + 1 < ntiles) issue_tile(t + 1);
+            mbar_wait(bar_s + 8u * (n & 1u), (n >> 1) & 1u);
+            const uint32_t my_row = side_tile_s<G>(S, n & 1u) + (uint32_t)lane * Geo::kTileRow;
+            const uint4 b0 = lds_u128(my_row), b1 = lds_u128(my_row + 16u), b2 = lds_u128(my_row + 32u);
+#pragma unroll
+            for (int ki = 0; ki < 2; ki++) {
+              uint32_t pl[G][4];
+              decode16(b, lut, pl[G - 1]);
+              take16(ki ? b1 : b0, ki ? b2 : b1, r0, pl[0]);
+              emit_elements<G>(pl, rot, stage, lane, (tr * 2 + ki) * G);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const uint4 v = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
+            *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
+          }
+          __syncwarp();
+        }
+        tiles_done += ntiles;
+        if (live && !window_exact(b)) atomicOr(&cfg.ctrl->error, kErrCorrupt);
+        continue;
+      }
+    }
     // ================= cp.async / LDS + STG path =================
     // ---- the other planes: groups 0 .. G-2 ----
     SidePlane side[NS];
@@ -1161,7 +1228,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
         nb += side[g].step;
         // block 2 waits in slot 0 (committed and waited for by the first decode16 group)
         side[g].swz = kSideSlots == 2 ? (((uint32_t)lane >> 2) & 1u) : (((uint32_t)lane >> 1) & 3u);
-        side[g].slots_s = side_slots_s<G, PB>(S, g) + 16u * kSideSlots * (uint32_t)lane;
+        side[g].slots_s = side_slots_s<G>(S, g) + 16u * kSideSlots * (uint32_t)lane;
         cp_async16_s(side_slot(side[g], 2u), (side[g].step && nb > hi_block) ? hi_block : nb);
       }
       cp_async_commit();

@@ -134,7 +134,8 @@ bool byte_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows
 }
 
 struct Knobs {
-  int tma = 1, grid_mode = 0, warps_per_sm = 0;
+  int tma = 2, grid_mode = 1, warps_per_sm = 0;  // tma: 1 = bulk-tensor stores of the output rows, 2 = bulk-tensor tiles for the side plane.
+                                                 // measured: bulk stores and a persistent grid are 3-4 % slower (profiles/r2_decode_probe.txt)
   long long sync_max = -1;  // chunks up to which k_huf_decode_sync replaces the one-thread-per-bitstream kernels (-1: default)
   size_t smem_pad = 0;
 };
@@ -176,7 +177,8 @@ inline uint64_t num_chunks(size_t n, size_t chunk) { return (n + chunk - 1) / ch
 // workspace.  The "full" size gives every chunk a pool slot (faster for streams that are all
 // general chunks, e.g. fp32 tensors upcast from bf16).
 constexpr uint64_t kDefaultSlots = 64;
-constexpr uint64_t kSyncDefaultMaxChunks = 3072;  // measured crossover with the one-thread-per-bitstream kernels (768 MiB of 256 KiB chunks)
+constexpr uint64_t kSyncDefaultMaxChunks = 2048;  // measured crossover with the one-thread-per-bitstream kernels: 256 MiB 0.78 vs 1.5 ms,
+                                                  // 1 GiB 2.5 vs 1.5 ms (profiles/r2_sweep_1gpu.jsonl)
 struct DecWs {
   size_t items_off, mode_off, slot_off, rlist_off, olist_off, hlist_off, fill_off, planes_off, pstride, fixed;
 };
@@ -412,10 +414,22 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
       if (cfg.k_full >= (uint64_t)kDecItemsPerWarp && chunk >= 2048 && (chunk / 4) * 4 == chunk) {
         if (byte_map_2d(&maps.out, d_out, chunk / 4, 4 * cfg.k_full, chunk / 4, 128, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE)) {
           cfg.tma_flags |= kTmaOut;
+        if (G == 2) {
+          // the raw byte plane of group 0 as rows of one quarter plane each, 16 bytes longer than the pitch: a box
+          // starts at the 16-byte boundary below the byte it needs (the payload is not aligned inside the stream)
+          const uint64_t seg = chunk / G / 4;
+          const uint8_t* base = (const uint8_t*)d_body + cfg.side_pred[0] - cfg.side_r0[0];
+          if (seg >= 64 && body_len >= cfg.side_pred[0] + 4 * cfg.k_full * seg &&
+              byte_map_2d(&maps.side[0], base, seg + 16, 4 * cfg.k_full, seg, FusedGeom<2>::kTileRow, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+            cfg.tma_flags |= kTmaSide;
+        }
         }
       }
       // tuning knobs for experiments (tools/decode_probe.py); unset in normal use
-      if (!kn.tma) cfg.tma_flags = 0;
+      cfg.tma_flags &= (uint32_t)kn.tma;
+      if (getenv("ZIPNN_B200_DEBUG")) fprintf(stderr, "[zipnn_b200] fused decode: K=%llu k_full=%llu tma_flags=%u side_r0=%u encoder=%p\n", (unsigned long long)K,
+                                              (unsigned long long)cfg.k_full, cfg.tma_flags, cfg.side_r0[0], (void*)tensor_map_encoder());
       ScopedTimer tm(kKHufDecode, st);
       int rc = dispatch_G(G, [&](auto g) -> int {
         constexpr int GG = decltype(g)::value;

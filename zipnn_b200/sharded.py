@@ -85,7 +85,7 @@ def _p2p(ops):
 
 # ----------------------------------------------------------------------------------------------
 def gather_stream(local_stream: torch.Tensor, local_hdr_len: int, G: int, K_local: int, n_local: int,
-                  global_header: bytes, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+                  global_header: bytes, dst: int = 0, group=None, chunk: Optional[int] = None) -> Optional[torch.Tensor]:
     """Merge per-rank streams (each covering a contiguous chunk range, in rank order) into the
     single stream the reference would have produced for the concatenated input.
 
@@ -104,6 +104,16 @@ def gather_stream(local_stream: torch.Tensor, local_hdr_len: int, G: int, K_loca
     allv = [v.cpu().tolist() for v in allv]
     Ks = [v[0] for v in allv]
     ns = [v[1] for v in allv]
+    # Shards must be cut at chunk boundaries (`byte_range`): a short chunk in the middle would give a stream the
+    # reference cannot decode.  Only the last non-empty rank may end with a ragged chunk; no rank may follow an empty one.
+    nonempty = [r for r in range(world) if ns[r]]
+    if nonempty and nonempty != list(range(len(nonempty))):
+        raise ValueError("sharded compress: an empty shard precedes a non-empty one; use zipnn_b200.sharded.byte_range to cut shards")
+    if chunk:
+        for r in nonempty[:-1]:
+            if ns[r] % chunk or Ks[r] * chunk != ns[r]:
+                raise ValueError(f"sharded compress: rank {r}'s shard ({ns[r]} bytes) is not a whole number of {chunk}-byte chunks; "
+                                 "use zipnn_b200.sharded.byte_range to cut shards")
     tot = [[v[2 + g] for g in range(G)] for v in allv]   # tot[r][g]
     K = sum(Ks)
     H = len(global_header)
@@ -283,7 +293,7 @@ class ShardedZipNN:
             global_shape = (int(cnt.item()),)
         ext = zipnn_pack_shape(tuple(global_shape)) if self.kw.get("input_format", "torch") != "byte" else b""
         assert world >= 1
-        return gather_stream(stream, HEADER_LEN, plan["num_buf"], K_local, n_local, bytes(gh) + ext, dst, self.group)
+        return gather_stream(stream, HEADER_LEN, plan["num_buf"], K_local, n_local, bytes(gh) + ext, dst, self.group, chunk=plan["chunk"])
 
     def decompress(self, stream: Optional[torch.Tensor], src: int = 0, device=None) -> torch.Tensor:
         from .util_torch import torch_dtype_of_code, zipnn_unpack_shape

@@ -44,6 +44,25 @@ def _as_u8_numpy(data) -> np.ndarray:
     return np.frombuffer(data, dtype=np.uint8)
 
 
+def _xor_bytes(a, b):
+    """Delta step (reference: np.bitwise_xor on host bytes, zipnn/zipnn.py:636-640, 997-1004).  If either side
+    lives on a GPU the XOR runs there and a CUDA uint8 tensor comes back; otherwise a numpy array."""
+    ta, tb = isinstance(a, torch.Tensor) and a.is_cuda, isinstance(b, torch.Tensor) and b.is_cuda
+    if ta or tb:
+        dev = a.device if ta else b.device
+
+        def dev_u8(x):
+            if isinstance(x, torch.Tensor):
+                x = x.detach().contiguous().reshape(-1)
+                return (x if x.dtype == torch.uint8 else x.view(torch.uint8)).to(dev, non_blocking=True)
+            return torch.from_numpy(np.array(_as_u8_numpy(x), copy=True)).to(dev, non_blocking=True)
+        ua, ub = dev_u8(a), dev_u8(b)
+        if ua.numel() != ub.numel():
+            raise ValueError("Length of delta file has to match the length of the original file.")
+        return torch.bitwise_xor(ua, ub)
+    return np.bitwise_xor(_as_u8_numpy(a), _as_u8_numpy(b))
+
+
 def _layout_for_dtype(code: int):
     """(bit_reorder, byte_reorder, num_buf) per dtype: reference zipnn/zipnn.py:788-815."""
     if code in (FLOAT8_E4M3FN, FLOAT8_E5M2):
@@ -196,16 +215,54 @@ class ZipNN:
             # independent frames of `streaming_chunk` input bytes (zipnn/zipnn.py:612-635)
             src = _as_u8_numpy(data)
             dlt = _as_u8_numpy(delta_second_data) if delta_second_data is not None else None
+            if dlt is not None:
+                src = np.bitwise_xor(src, dlt)
+            fast = self._compress_frames_at_once(src)
+            if fast is not None:
+                return fast
             out = bytearray()
             for off in range(0, src.size, self.streaming_chunk):
-                piece = src[off: off + self.streaming_chunk]
-                if dlt is not None:
-                    piece = np.bitwise_xor(piece, dlt[off: off + self.streaming_chunk])
-                out.extend(self.compress_torch_numpy_byte(piece))
+                out.extend(self.compress_torch_numpy_byte(src[off: off + self.streaming_chunk]))
             return out
         if delta_second_data is not None:
-            data = np.bitwise_xor(_as_u8_numpy(data), _as_u8_numpy(delta_second_data))
+            data = _xor_bytes(data, delta_second_data)
         return self.compress_torch_numpy_byte(data)
+
+    def _compress_frames_at_once(self, src: np.ndarray):
+        """All streaming frames from ONE pass of the codec.  A frame is the stream of `streaming_chunk` input
+        bytes compressed alone (zipnn/zipnn.py:612-635); when a frame is a whole number of chunks, that is
+        the frame's rows of the type / size tables (sizes rebased to the frame) and its slices of the
+        per-group payload of the stream of the WHOLE input, because chunks are coded independently.  One H2D
+        copy and one set of kernel launches instead of one per MiB.  -> bytearray, or None (caller loops)."""
+        code = dtype_code(self.bytearray_dtype)
+        _, _, num_buf = _layout_for_dtype(code)
+        chunk = self.compression_chunk if num_buf != 1 else min(HUF_MAX_BLOCK, self.compression_chunk)
+        n = src.size
+        if n == 0 or self.streaming_chunk % chunk or self.streaming_chunk < chunk:
+            return None
+        whole = np.frombuffer(self.compress_torch_numpy_byte(src), dtype=np.uint8)
+        H, G = HEADER_LEN, num_buf
+        K = (n + chunk - 1) // chunk
+        types = whole[H: H + G * K].reshape(G, K)
+        cum = np.frombuffer(whole[H + G * K: H + 9 * G * K].tobytes(), dtype="<u8").reshape(G, K).astype(np.int64)
+        payload0 = H + 9 * G * K
+        base = payload0 + np.concatenate([[0], np.cumsum(cum[:, -1])[:-1]])
+        per = self.streaming_chunk // chunk
+        out = bytearray()
+        hdr = bytearray(whole[:H].tobytes())
+        for c0 in range(0, K, per):
+            c1 = min(K, c0 + per)
+            lo = cum[:, c0 - 1] if c0 else np.zeros(G, dtype=np.int64)
+            hi = cum[:, c1 - 1]
+            flen = H + 9 * G * (c1 - c0) + int((hi - lo).sum())
+            hdr[16:24] = int(min(n, c1 * chunk) - c0 * chunk).to_bytes(8, "little")
+            hdr[24:32] = int(flen).to_bytes(8, "little")
+            out.extend(hdr)
+            out.extend(np.ascontiguousarray(types[:, c0:c1]).tobytes())
+            out.extend((cum[:, c0:c1] - lo.reshape(G, 1)).astype("<u8").tobytes())
+            for g in range(G):
+                out.extend(whole[int(base[g] + lo[g]): int(base[g] + hi[g])].tobytes())
+        return out
 
     def compress_torch_numpy_byte(self, data, lossy_compressed_type=None, lossy_compressed_factor=None):
         """dtype dispatch + byte view of the input: zipnn/zipnn.py:748-867."""
@@ -225,6 +282,8 @@ class ZipNN:
 
         if fmt == EnumFormat.TORCH.value:
             t = data.detach().contiguous().reshape(-1)
+            if t.numel() == 0:   # (an empty tensor may carry a zero stride, which view() refuses)
+                t = torch.empty(0, dtype=t.dtype, device=t.device)
             flat = t.view(torch.uint8) if t.dtype != torch.uint8 else t
         elif fmt == EnumFormat.NUMPY.value:
             flat = torch.from_numpy(np.ascontiguousarray(data).reshape(-1).view(np.uint8))
@@ -302,6 +361,13 @@ class ZipNN:
             if isinstance(stream, torch.Tensor):
                 stream = stream.cpu().numpy()
             dlt = _as_u8_numpy(delta_second_data) if delta_second_data is not None else None
+            fast = self._decompress_frames_at_once(stream)
+            if fast is not None:
+                if dlt is not None:
+                    if fast.size != dlt.size:
+                        raise ValueError("Length of delta file has to match the length of the decompressed file.")
+                    fast = np.bitwise_xor(fast, dlt)
+                return bytearray(fast.tobytes())
             out = bytearray()
             off, doff = 0, 0
             while off < stream.size:
@@ -322,12 +388,66 @@ class ZipNN:
 
         result = self.decompress_bin(stream, head=head)
         if delta_second_data is not None:
-            dec = _as_u8_numpy(result)
-            dlt = _as_u8_numpy(delta_second_data)
-            if dec.size != dlt.size:
+            on_gpu = (isinstance(result, torch.Tensor) and result.is_cuda) or (isinstance(delta_second_data, torch.Tensor) and delta_second_data.is_cuda)
+            nres = result.numel() * result.element_size() if isinstance(result, torch.Tensor) else len(_as_u8_numpy(result))
+            ndlt = delta_second_data.numel() * delta_second_data.element_size() if isinstance(delta_second_data, torch.Tensor) else len(_as_u8_numpy(delta_second_data))
+            if nres != ndlt:
                 raise ValueError("Length of delta file has to match the length of the decompressed file.")
-            return np.bitwise_xor(dec, dlt).tobytes()
+            x = _xor_bytes(result, delta_second_data)
+            return x if on_gpu else x.tobytes()
         return result
+
+    def _decompress_frames_at_once(self, stream: np.ndarray):
+        """Every frame of a streaming file in one batched decode (zipnn_b200_decompress_batch): one H2D copy of
+        the file, one launch per kernel, one D2H copy -- instead of a copy, five launches and two
+        synchronisations per 1 MiB frame.  -> uint8 array, or None when a frame does not fit the fast path."""
+        H = HEADER_LEN
+        frames = []
+        off = doff = 0
+        total = stream.size
+        while off < total:
+            if off + H > total:
+                raise RuntimeError("corrupt ZipNN streaming frame")
+            hd = stream[off: off + H].tobytes()
+            flen = int.from_bytes(hd[24:32], "little")
+            if hd[0:2] != b"ZN" or flen < H or off + flen > total:
+                raise RuntimeError("corrupt ZipNN streaming frame")
+            z = ZipNN(input_format="byte", bytearray_dtype=self.bytearray_dtype)
+            z._retrieve_header(hd)
+            num_buf = z._num_buf_of_dtype()
+            chunk = z.compression_chunk if num_buf != 1 else min(HUF_MAX_BLOCK, z.compression_chunk)
+            if doff % 16:
+                return None        # (a frame whose output would not start on a 16-byte boundary: per-frame loop)
+            frames.append((off + H, flen - H, num_buf, z._bit_reorder, z._byte_reorder, chunk, z.original_len, doff))
+            off += flen
+            doff += z.original_len
+        if not frames:
+            return np.empty(0, dtype=np.uint8)
+        _native.require_cuda()
+        L = _native.lib()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        src_t = _host_tensor(np.ascontiguousarray(stream))
+        dbuf = torch.empty(64 + total + 16, dtype=torch.uint8, device=dev)
+        dbuf[64: 64 + total].copy_(src_t, non_blocking=True)
+        out = torch.empty(max(doff, 1), dtype=torch.uint8, device=dev)
+        arr = (_native.BatchItem * len(frames))()
+        for i, (boff, blen, num_buf, bits, bytes_mode, chunk, n, o) in enumerate(frames):
+            arr[i].d_body = dbuf.data_ptr() + 64 + boff
+            arr[i].body_len = blen
+            arr[i].num_buf, arr[i].bits_mode, arr[i].bytes_mode = num_buf, bits, bytes_mode
+            arr[i].chunk, arr[i].orig = chunk, n
+            arr[i].d_out = out.data_ptr() + o if n else None
+        wsz = C.c_size_t(0)
+        _native.check(L.zipnn_b200_decompress_batch_workspace_size(arr, len(frames), C.byref(wsz)))
+        ws = torch.empty(wsz.value, dtype=torch.uint8, device=dev)
+        rc = L.zipnn_b200_decompress_batch(arr, len(frames), ws.data_ptr(), ws.numel(), _cuda_stream_handle(), 1)
+        if rc == _native.E_CORRUPT:
+            raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
+        _native.check(rc)
+        host = _host_out(doff, None)
+        host.copy_(out[:doff], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
 
     def _num_buf_of_dtype(self) -> int:
         code = self.dtype
@@ -783,249 +903,41 @@ def _host_out(nbytes: int, out):
 
 def _compress_host(flat_u8, header: bytes, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int,
                    threshold: float, out=None):
-    """Host bytes in, host bytes out: H2D copy, GPU codec, D2H copy of exactly the stream."""
+    """Host bytes in, host bytes out through `zipnn_b200_compress_host` (include/zipnn_b200.h): the library
+    moves the input through the device slab by slab, with the copies in both directions and the kernels
+    overlapped.  Pinned buffers (torch pin_memory) get the full PCIe rate; any host memory works."""
     _native.require_cuda()
-    src = _host_tensor(flat_u8)
-    if src.numel() >= PIPELINE_MIN_BYTES and src.numel() > PIPELINE_SLAB_BYTES:
-        return _compress_host_pipelined(src, header, num_buf, bits_mode, bytes_mode, chunk, threshold, out)
-    dev_in = torch.empty(src.numel(), dtype=torch.uint8, device="cuda")
-    dev_in.copy_(src, non_blocking=True)
-    stream = _compress_device(dev_in, header, num_buf, bits_mode, bytes_mode, chunk, threshold)
-    host = _host_out(stream.numel(), out)
-    host.copy_(stream, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return memoryview(host.numpy())
-
-
-def _compress_host_pipelined(src: torch.Tensor, header: bytes, G: int, bits_mode: int, bytes_mode: int, chunk: int,
-                             threshold: float, out=None):
-    """Large host inputs go through the device slab by slab so that PCIe runs in both directions at
-    once.  Chunks are independent (a slab compressed alone yields the same per-chunk payloads, the
-    construction zipnn_b200.sharded uses across GPUs), and in the stream layout
-    `[header][types][cum][group 0 payloads][group 1 payloads]...` (csrc/zipnn_core.c:105-244) the
-    position of group 0's payload of a slab depends only on the slabs before it.  So while slab i+1
-    is on its way in, slab i is compressed and its group-0 payload (the raw sign/mantissa plane of
-    bf16: 3/4 of the stream) is already on its way out to its final place; the other groups wait on
-    the device until group 0's total is known.  The tables and the header are assembled on the host."""
     L = _native.lib()
+    src = _host_tensor(flat_u8)
     n = src.numel()
-    K = (n + chunk - 1) // chunk
-    per = max(1, min(PIPELINE_SLAB_BYTES, PIPELINE_COMPRESS_SLAB_BYTES) // chunk)
-    slabs = [(c0, min(K, c0 + per)) for c0 in range(0, K, per)]
-    hdr_len = len(header)
-    payload0 = hdr_len + 9 * G * K
     if out is None:
-        host = _host_out(_native.compress_bound(n, G, chunk, hdr_len), None)
-    else:   # the size is not known in advance: use whatever room the caller gave, check as we go
-        host = _host_out(0, out)
+        host = _host_out(_native.compress_bound(n, num_buf, chunk, len(header)), None)
+    else:   # the size is not known in advance: use whatever room the caller gave, the library checks as it goes
         host = out.detach().reshape(-1)
         host = host if host.dtype == torch.uint8 else host.view(torch.uint8)
-    cap = host.numel()
-    if cap < payload0:
+        if host.is_cuda or not host.is_contiguous():
+            raise ValueError("out= must be a contiguous CPU tensor with room for the result")
+    hdr = (C.c_char * len(header)).from_buffer_copy(header)
+    out_len = C.c_size_t(0)
+    rc = L.zipnn_b200_compress_host(src.data_ptr() if n else None, n, hdr, len(header), num_buf, bits_mode, bytes_mode, chunk, threshold,
+                                    host.data_ptr(), host.numel(), C.byref(out_len))
+    if rc == _native.E_CAPACITY:
         raise ValueError("out= must be a contiguous CPU tensor with room for the result")
-    dev = torch.device("cuda", torch.cuda.current_device())
-    slab_hdr = bytes(32)
-    slab_bytes_max = per * chunk
-    sbound = (_native.compress_bound(slab_bytes_max, G, chunk, 32) + 255) & ~255
-    held = torch.empty(sbound * len(slabs), dtype=torch.uint8, device=dev)       # every slab's stream stays on the device
-    nst = 2
-    streams = [torch.cuda.Stream() for _ in range(nst)]
-    out_stream = torch.cuda.Stream()
-    cur = torch.cuda.current_stream()
-    dins = [torch.empty(slab_bytes_max, dtype=torch.uint8, device=dev) for _ in range(nst)]
-    wss = [torch.empty(_native.compress_workspace_size(slab_bytes_max, G, chunk), dtype=torch.uint8, device=dev) for _ in range(nst)]
-    hdr_c = (C.c_char * 32).from_buffer_copy(slab_hdr)
-    types_all = np.empty((G, K), dtype=np.uint8)
-    cum_all = np.empty((G, K), dtype=np.int64)
-    run = np.zeros(G, dtype=np.int64)              # bytes of each group in the slabs before this one
-    slab_off = []                                  # per slab: payload offset inside `held` of each group, sizes
-    # Groups behind group 0 leave early too, on the bet that every group in front of them stays raw
-    # (the mantissa planes of float weights always do): then their base is known in advance.  A lost
-    # bet costs one more copy of that group at the end.
-    pred_tot = np.array([n // G + (1 if g < n % G else 0) for g in range(G)], dtype=np.int64)
-    pred_base = payload0 + np.concatenate([[0], np.cumsum(pred_tot)[:-1]])
-    all_raw = np.ones(G, dtype=bool)
-    early = [False] * G                            # group g was (so far) copied out at pred_base[g]
-    for st in streams:
-        st.wait_stream(cur)
-    out_stream.wait_stream(cur)
-
-    def upload(i):
-        c0, c1 = slabs[i]
-        b0, b1 = c0 * chunk, min(n, c1 * chunk)
-        with torch.cuda.stream(streams[i % nst]):
-            dins[i % nst][: b1 - b0].copy_(src[b0:b1], non_blocking=True)
-
-    upload(0)
-    for i, (c0, c1) in enumerate(slabs):
-        k = i % nst
-        Ks = c1 - c0
-        nb = min(n, c1 * chunk) - c0 * chunk
-        if i + 1 < len(slabs):
-            upload(i + 1)                          # in flight while slab i is compressed and copied out
-        dst = held[i * sbound: (i + 1) * sbound]
-        out_len = C.c_size_t(0)
-        _native.check(L.zipnn_b200_compress(dins[k].data_ptr(), nb, hdr_c, 32, G, bits_mode, bytes_mode, chunk, threshold,
-                                            dst.data_ptr(), sbound, C.byref(out_len), wss[k].data_ptr(), wss[k].numel(),
-                                            streams[k].cuda_stream))        # returns when the slab's stream is complete
-        with torch.cuda.stream(streams[k]):
-            meta = dst[32: 32 + 9 * G * Ks].cpu().numpy()
-        types_all[:, c0:c1] = meta[: G * Ks].reshape(G, Ks)
-        cs = meta[G * Ks:].view("<u8").reshape(G, Ks).astype(np.int64)
-        cum_all[:, c0:c1] = cs + run.reshape(G, 1)
-        tot = cs[:, -1]
-        offs = 32 + 9 * G * Ks + np.concatenate([[0], np.cumsum(tot)[:-1]])
-        if 32 + 9 * G * Ks + int(tot.sum()) != out_len.value:
-            raise RuntimeError("zipnn_b200: inconsistent slab stream")
-        slab_off.append((offs, tot, run.copy()))
-        all_raw &= ~np.any(types_all[:, c0:c1] != 0, axis=1)
-        with torch.cuda.stream(out_stream):
-            for g in range(G):
-                if g and not bool(np.all(all_raw[:g])):
-                    early[g] = False
-                    continue
-                a = int(pred_base[g] + run[g])             # exact for group 0, a bet for the others
-                if a + int(tot[g]) > cap:
-                    if g == 0:
-                        raise ValueError("out= must be a contiguous CPU tensor with room for the result")
-                    early[g] = False
-                    continue
-                if i == 0:
-                    early[g] = True
-                if tot[g] and (g == 0 or early[g]):
-                    host[a: a + int(tot[g])].copy_(dst[int(offs[g]): int(offs[g]) + int(tot[g])], non_blocking=True)
-        run += tot
-    base = payload0 + np.concatenate([[0], np.cumsum(run)[:-1]])
-    total = payload0 + int(run.sum())
-    if total > cap:
-        raise ValueError("out= must be a contiguous CPU tensor with room for the result")
-    with torch.cuda.stream(out_stream):
-        for g in range(1, G):
-            if early[g] and int(base[g]) == int(pred_base[g]):
-                continue                                   # already in place
-            for i in range(len(slabs)):
-                offs, tot, before = slab_off[i]
-                if tot[g]:
-                    a = int(base[g] + before[g])
-                    o = i * sbound + int(offs[g])
-                    host[a: a + int(tot[g])].copy_(held[o: o + int(tot[g])], non_blocking=True)
-    # header (total length at [24:32], csrc/zipnn_core.c:121) and the two tables, written by the host
-    hb = bytearray(header)
-    hb[24:32] = int(total).to_bytes(8, "little")
-    hv = host.numpy()
-    hv[:hdr_len] = np.frombuffer(bytes(hb), dtype=np.uint8)
-    hv[hdr_len: hdr_len + G * K] = types_all.reshape(-1)
-    hv[hdr_len + G * K: payload0] = cum_all.astype("<u8").reshape(-1).view(np.uint8)
-    out_stream.synchronize()
-    for st in streams:
-        cur.wait_stream(st)
-    return memoryview(hv[:total])
-
-
-# Host streams at least this large are decoded slab by slab on two CUDA streams, so the H2D
-# copy of one slab overlaps the decode of the previous one and the D2H copy of the one before
-# (PCIe is full duplex; a 16 GiB bf16 round trip is ~97% copy time).  Tests lower both knobs.
-PIPELINE_MIN_BYTES = 64 << 20
-PIPELINE_SLAB_BYTES = 256 << 20
-PIPELINE_COMPRESS_SLAB_BYTES = 128 << 20   # measured, 8 GiB bf16: compress 172 ms with 128 MiB slabs, 186 with 256; decompress the other way round
+    _native.check(rc)
+    return memoryview(host.numpy()[: out_len.value])
 
 
 def _decompress_host(body: np.ndarray, num_buf: int, bits_mode: int, bytes_mode: int, chunk: int, orig: int, out=None) -> torch.Tensor:
+    """Host stream in, host bytes out through `zipnn_b200_decompress_host`: chunk ranges of 256 MiB are a
+    stream of their own once their table rows are rebased, so the library decodes slab by slab on two
+    CUDA streams with the H2D copy, the kernels and the D2H copy of neighbouring slabs overlapped."""
     _native.require_cuda()
     host = _host_out(orig, out)
     if orig == 0:
         return host
-    if orig >= PIPELINE_MIN_BYTES and orig > PIPELINE_SLAB_BYTES:
-        done = _decompress_host_pipelined(body, num_buf, bits_mode, bytes_mode, chunk, orig, host)
-        if done:
-            return host
     src = _host_tensor(np.ascontiguousarray(body))
-    # 64 leading bytes keep the word-granular stream readers inside the allocation
-    dev = torch.empty(src.numel() + 64 + 16, dtype=torch.uint8, device="cuda")
-    dev_body = dev[64: 64 + src.numel()]
-    dev_body.copy_(src, non_blocking=True)
-    dec = _decompress_device(dev_body, num_buf, bits_mode, bytes_mode, chunk, orig)
-    host.copy_(dec, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    rc = _native.lib().zipnn_b200_decompress_host(src.data_ptr(), src.numel(), num_buf, bits_mode, bytes_mode, chunk, orig, host.data_ptr())
+    if rc == _native.E_CORRUPT:
+        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")   # reference: zipnn_core.c:1089
+    _native.check(rc)
     return host
-
-
-def _decompress_host_pipelined(body: np.ndarray, G: int, bits_mode: int, bytes_mode: int, chunk: int, orig: int,
-                               host: torch.Tensor) -> bool:
-    """Chunks are independent, so any chunk range [c0, c1) is a stream of its own once its rows of
-    the type/size tables are rebased (the same construction zipnn_b200.sharded uses across GPUs).
-    Returns False if the stream turns out to need the general-path workspace (caller falls back)."""
-    L = _native.lib()
-    K = (orig + chunk - 1) // chunk
-    body = np.ascontiguousarray(body)
-    if body.size < 9 * G * K:
-        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
-    types = body[: G * K].reshape(G, K)
-    cum = np.frombuffer(body[G * K: 9 * G * K].tobytes(), dtype="<u8").reshape(G, K).astype(np.int64)
-    payload0 = 9 * G * K
-    group_tot = cum[:, -1]
-    if np.any(np.diff(cum, axis=1) < 0) or np.any(cum[:, 0] < 0) or payload0 + int(group_tot.sum()) > body.size:
-        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
-    base = np.concatenate([[0], np.cumsum(group_tot)[:-1]]).astype(np.int64) + payload0
-    per = max(1, PIPELINE_SLAB_BYTES // chunk)
-    slabs = [(c0, min(K, c0 + per)) for c0 in range(0, K, per)]
-    src_t = _host_tensor(body)
-    nst = 2
-    streams = [torch.cuda.Stream() for _ in range(nst)]
-    cur = torch.cuda.current_stream()
-    slab_bytes_max = per * chunk
-    # per-stream device buffers: [64 pad | local body], decoded slab, workspace
-    lbuf = [torch.empty(64 + 9 * G * per + slab_bytes_max + 9 * G * per + 64, dtype=torch.uint8, device="cuda") for _ in range(nst)]
-    obuf = [torch.empty(slab_bytes_max, dtype=torch.uint8, device="cuda") for _ in range(nst)]
-    wsz = _native.decompress_workspace_size(slab_bytes_max, G, chunk)
-    wbuf = [torch.empty(wsz, dtype=torch.uint8, device="cuda") for _ in range(nst)]
-    stage = [torch.empty(9 * G * per + 64, dtype=torch.uint8, pin_memory=True) for _ in range(nst)]
-    staged_evt = [None] * nst
-    errs = torch.zeros(len(slabs), dtype=torch.int32, device="cuda")
-    rc_bad = 0
-    for i, (c0, c1) in enumerate(slabs):
-        k = i % nst
-        st = streams[k]
-        Ks = c1 - c0
-        b0, b1 = c0 * chunk, min(orig, c1 * chunk)
-        lo = cum[:, c0 - 1] if c0 else np.zeros(G, dtype=np.int64)
-        sizes = cum[:, c1 - 1] - lo
-        tables = np.empty(9 * G * Ks, dtype=np.uint8)
-        tables[: G * Ks] = types[:, c0:c1].reshape(-1)
-        tables[G * Ks:] = (cum[:, c0:c1] - lo.reshape(G, 1)).astype("<u8").reshape(-1).view(np.uint8)
-        if staged_evt[k] is not None:
-            staged_evt[k].synchronize()          # the previous H2D out of this staging buffer is done
-        stage[k][: tables.size].copy_(torch.from_numpy(tables))
-        st.wait_stream(cur)
-        with torch.cuda.stream(st):
-            dbody = lbuf[k][64:]
-            dbody[: tables.size].copy_(stage[k][: tables.size], non_blocking=True)
-            staged_evt[k] = torch.cuda.Event()
-            staged_evt[k].record(st)
-            at = tables.size
-            for g in range(G):
-                ln = int(sizes[g])
-                if ln:
-                    s0 = int(base[g] + lo[g])
-                    dbody[at: at + ln].copy_(src_t[s0: s0 + ln], non_blocking=True)
-                    at += ln
-            rc = L.zipnn_b200_decompress(dbody.data_ptr(), at, G, bits_mode, bytes_mode, chunk, b1 - b0,
-                                         obuf[k].data_ptr(), wbuf[k].data_ptr(), wbuf[k].numel(), st.cuda_stream, 0)
-            if rc:
-                rc_bad = rc
-                break
-            errs[i: i + 1].copy_(wbuf[k][:4].view(torch.int32), non_blocking=True)
-            host[b0:b1].copy_(obuf[k][: b1 - b0], non_blocking=True)
-    for st in streams:
-        cur.wait_stream(st)
-    cur.synchronize()
-    if rc_bad:
-        _native.check(rc_bad)
-    flags = int(np.bitwise_or.reduce(errs.cpu().numpy())) if len(slabs) else 0
-    if flags & 1:
-        raise RuntimeError("Thread processing failed: corrupt ZipNN stream")
-    if flags & 2:
-        _native.check(_native.E_UNSUPPORTED)
-    if flags & 4:
-        return False  # many multi-group chunks: let the one-shot path size the full workspace
-    return True
