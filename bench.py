@@ -509,7 +509,7 @@ def run_ours(args, rank, local_rank, world):
             e_ms = float(tt.item())
         e2e = {"value": round(world * eb / (e_ms * 1e-3) / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": world * (eb + c_e2e),
                "d2h_bytes_per_step": world * (c_e2e + eb), "ms_per_step": round(e_ms, 2), "bytes_per_gpu": eb,
-               "api": "zipnn_b200.ZipNN(input_format='torch').compress(pinned cpu tensor, out=pinned) / .decompress(host stream, out=pinned): H2D copy, zipnn_b200_compress / _decompress, D2H copy"}
+               "api": "zipnn_b200.ZipNN(input_format='torch').compress(pinned cpu tensor, out=pinned) / .decompress(host stream, out=pinned) -> C ABI zipnn_b200_compress_host / zipnn_b200_decompress_host (include/zipnn_b200.h): the library moves the data through the device slab by slab, H2D copy, kernels and D2H copy overlapped"}
         e2e["numa"] = numa
         # per-rank one-way PCIe rates of the e2e region (the limiter at 8 GPUs is host memory / root ports, not the codec)
         del ht, hs_buf, hd_buf

@@ -52,4 +52,6 @@ def make_input(spec: dict):
 def raw_bytes(data) -> bytes:
     if isinstance(data, (bytes, bytearray)):
         return bytes(data)
+    if data.numel() == 0:
+        return b""
     return data.contiguous().reshape(-1).view(torch.uint8).numpy().tobytes()

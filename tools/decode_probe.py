@@ -35,14 +35,21 @@ def main():
         for k in keys:
             os.environ.pop(k, None)
         os.environ.update(cfg)
-        for _ in range(2):
-            d = ZipNN(input_format="torch").decompress(s)
-        ok = bool(torch.equal(d.view(torch.uint8), t.view(torch.uint8)))
-        del d
+        ok = None
+        try:
+            for _ in range(2):
+                d = ZipNN(input_format="torch").decompress(s)
+            ok = bool(torch.equal(d.view(torch.uint8), t.view(torch.uint8)))
+            del d
+        except RuntimeError as exc:      # timing experiments that decode wrongly on purpose
+            ok = f"raised: {exc}"[:60]
         _native.timing_enable(True)
         for _ in range(3):
-            d = ZipNN(input_format="torch").decompress(s)
-            del d
+            try:
+                d = ZipNN(input_format="torch").decompress(s)
+                del d
+            except RuntimeError:
+                pass
         kt = _native.timing_collect()
         _native.timing_enable(False)
         ms, cnt = kt["k_huf_decode_fused"]

@@ -397,9 +397,9 @@ struct LutTwo {
   uint32_t x_long;
   __device__ __forceinline__ int32_t get(uint32_t x) const {
     const uint32_t idx = x & 0x7FFu;
-    int32_t e = lds_s16(((x >> 2) & 0x1FEu) | prim_s);  // 2 * (top 8 of the 11 bits); every primary is 512-byte aligned
-    if (idx < x_long) e = lds_s16(tail_s + idx + idx);
-    return e;
+    const uint32_t a_prim = ((x >> 2) & 0x1FEu) | prim_s;  // 2 * (top 8 of the 11 bits); every primary is 512-byte aligned
+    const uint32_t a_tail = tail_s + idx + idx;
+    return lds_s16(idx < x_long ? a_tail : a_prim);      // one load, address selected (see LutCol)
   }
 };
 
@@ -419,11 +419,14 @@ struct LutCol {
   uint32_t x_long;
   __device__ __forceinline__ int32_t get(uint32_t x) const {
     const uint32_t idx = x & 0x7FFu;
-    int32_t e = lds_s16((x & 0x7C0u) | col_s);
-#ifndef ZB_EXP_NOTAIL   // timing experiment only (wrong symbols for long codes)
-    if (idx < x_long) e = lds_s16(tail_s + idx + idx);
-#endif
-    return e;
+    // ONE load per symbol: the address is SELECTED between the lane's column and the chunk's tail.  The
+    // kernel is bound by the number of LSU instructions it issues (~2.6 cycles each per SM, whatever their
+    // width, conflicts or predicate: removing the tail lookup altogether -- wrong, timing only -- gave
+    // 8.76 -> 7.44 ms), not by ALU work or by the length of the dependent chain, so one more SEL in front
+    // of the load is cheaper than a second, predicated, load behind it.
+    const uint32_t a_col = (x & 0x7C0u) | col_s;
+    const uint32_t a_tail = tail_s + idx + idx;
+    return lds_s16(idx < x_long ? a_tail : a_col);
   }
 };
 
