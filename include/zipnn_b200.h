@@ -50,7 +50,7 @@ extern "C" {
 #define ZIPNN_B200_E_UNSUPPORTED 5 /* valid stream using a table log of 12 (never produced by
                                      the reference encoder, which asks for 11)                   */
 
-int zipnn_b200_version(void);                 /* 0x000100 = 0.1.0 */
+int zipnn_b200_version(void);                 /* 0x000200 = 0.2.0 */
 const char* zipnn_b200_strerror(int status);
 int zipnn_b200_last_cuda_error(void);         /* cudaError_t of the last failing runtime call */
 int zipnn_b200_sm_count(void);                /* multiprocessor count of the current device   */
@@ -59,10 +59,11 @@ int zipnn_b200_sm_count(void);                /* multiprocessor count of the cur
 /* Upper bound of the whole stream (python header included). */
 int zipnn_b200_compress_bound(size_t n, int num_buf, size_t chunk, size_t hdr_len, size_t* out);
 int zipnn_b200_compress_workspace_size(size_t n, int num_buf, size_t chunk, size_t* out);
-/* Decompress workspace.  The normal size covers streams in which every chunk has at most one
- * Huffman-coded byte group (what float tensors produce) plus 64 chunks of the general kind;
- * if a stream needs more, zipnn_b200_decompress returns ZIPNN_B200_E_CAPACITY and the caller
- * retries with the `_full` size. */
+/* Decompress workspace.  The normal size decodes ANY stream in one call: chunks that need plane scratch
+ * (several Huffman-coded byte groups, a ragged tail) get one of 64 pool slots, decoded by whole-GPU
+ * kernels, and every further such chunk is taken in stream order by a few persistent CTAs that own 32
+ * more slots.  The `_full` size gives every chunk a pool slot: faster for streams in which EVERY chunk is
+ * of that kind (e.g. an fp32 tensor upcast from bf16), never required. */
 int zipnn_b200_decompress_workspace_size(size_t orig, int num_buf, size_t chunk, size_t* out);
 int zipnn_b200_decompress_workspace_size_full(size_t orig, int num_buf, size_t chunk, size_t* out);
 

@@ -70,7 +70,7 @@ def test_cabi_exports_every_declared_symbol():
 
 
 def test_cabi_sizing_without_gpu():
-    assert _native.lib().zipnn_b200_version() == 0x000100
+    assert _native.lib().zipnn_b200_version() == 0x000200
     # worst case: every plane raw -> header + 9 bytes of metadata per (group, chunk) + n
     assert _native.compress_bound(1 << 21, 2, 1 << 18, 34) == 34 + 9 * 2 * 8 + (1 << 21)
     assert _native.compress_bound(0, 2, 1 << 18, 32) == 32

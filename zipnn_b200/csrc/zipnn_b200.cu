@@ -221,7 +221,7 @@ int read_ctrl_error(void* d_ws, cudaStream_t st) {
 
 extern "C" {
 
-int zipnn_b200_version(void) { return 0x000100; }
+int zipnn_b200_version(void) { return 0x000200; }
 
 const char* zipnn_b200_strerror(int s) {
   switch (s) {
