@@ -33,6 +33,8 @@
 
 namespace zb {
 
+struct ItemTable;
+
 enum : uint32_t { kModePlain = 0, kModeFused = 1, kModeGeneral = 2, kModeSkip = 3, kModeOverflow = 4 };
 constexpr uint32_t kOverflowCtas = 32;  // persistent CTAs (each with private plane scratch) for general chunks beyond the slot pool
 constexpr uint32_t kFillBytes = 64;  // replicated RLE byte block per item (read with stride 0)
@@ -58,6 +60,7 @@ struct DecodeCfg {
   uint32_t ovf_slots;   // plane slots behind the pool, one per CTA of k_decode_overflow (0: none, an overflow is an error)
   uint32_t* olist;      // [K] chunks for k_decode_overflow, ctrl->overflow_count of them
   uint32_t* hlist;      // [G*K] coded items (g*K + c) for k_huf_decode_sync, ctrl->huf_count of them; nullptr: not used
+  struct ItemTable* tables;  // [G*K] parsed table descriptions, parallel to hlist (k_parse_tables)
   uint32_t tma_flags;   // kTmaOut | kTmaSide: which tensor maps of the fused kernel's TmaMaps argument are valid
   uint64_t k_full;      // chunks of full length (K, or K - 1 with a ragged last chunk)
   uint64_t side_pred[3];  // payload offset (inside body) of byte plane g's first item IF every group in front of it is all raw

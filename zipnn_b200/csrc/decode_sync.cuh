@@ -25,8 +25,9 @@
 //      the general regroup (several coded groups, ragged tail), copies the quarter plane to the
 //      chunk's workspace plane.
 // About 2.6 decode passes instead of 1, but over 256 threads per bitstream instead of 1: a 1 MiB
-// tensor is 16 CTAs x ~20 us instead of 16 threads x 1.5 ms.  One full 2^11-entry table per CTA
-// (built by 256 threads), so no two-level lookup.
+// tensor is 16 CTAs x tens of microseconds instead of 16 threads x 1.5 ms.  The bitstream is copied into shared
+// memory once and every pass reads it there; one full 2^11-entry table per CTA (built by 256 threads, from the
+// weights k_parse_tables extracted once per item), so no two-level lookup.
 #pragma once
 #include "decode.cuh"
 
@@ -35,20 +36,30 @@ namespace zb {
 constexpr int kSyncThreads = 256;
 constexpr uint32_t kSyncMinSegBits = 192;  // shorter segments only add overshoot work
 
+constexpr uint32_t kSyncStreamCap = 28u * 1024u;   // bitstream bytes kept in shared memory (bf16 ~10.6 KB, fp16 ~22, fp8 ~26)
+constexpr uint32_t kSyncPad = 32u;                // readable bytes below the stream's first aligned block
+
 struct SyncShared {
   uint16_t lut[kDecLutEntries];                    // full table: symbol | (-length << 8), replicated into 11 bits
-  __align__(16) uint8_t ring[kSyncThreads][kRingBytes];
+  // The whole bitstream, copied once by the CTA (aligned 16-byte blocks, so the stream keeps its offset mod 16):
+  // every pass of every thread reads it from here -- no per-thread ring, no cp.async, no refill latency on a
+  // re-seek.  A stream longer than the buffer (possible in the format, not seen in float tensors) falls back
+  // to the per-thread rings of the one-thread-per-bitstream kernels, which alias this buffer.
+  __align__(64) uint8_t sbuf[kSyncPad + kSyncStreamCap + 32];
   uint32_t stop[kSyncThreads];                     // bit offset where segment m's decode stopped
-  uint32_t count[kSyncThreads];                    // symbols of segment m; then their exclusive prefix
-  uint32_t warp_tot[kSyncThreads / 32];
   uint8_t weights[256];
-  int lg, hsize, nsym;
+  uint32_t warp_tot[kSyncThreads / 32];
   uint32_t cls_start[kHufLogMax + 2];              // index-space start of weight class w (11-bit space)
   uint32_t cls_count[kHufLogMax + 2];
   PlaneSrc src[4];
-  __align__(16) uint8_t plane[kHufBlockMax / 4 + 16];  // the decoded quarter plane; the tANS scratch of the parse aliases it
+  __align__(16) uint8_t plane[kHufBlockMax / 4 + 16];  // the decoded quarter plane
 };
-static_assert(sizeof(FseDec) <= kHufBlockMax / 4, "the parse scratch aliases the plane");
+static_assert(sizeof(((SyncShared*)0)->sbuf) >= kSyncThreads * kRingBytes, "the fallback rings alias the stream buffer");
+// Parsed table description of one coded item (k_parse_tables -> k_huf_decode_sync), in the workspace.
+struct ItemTable {
+  uint8_t weights[256];
+  int32_t hsize, lg, nsym, pad;
+};
 
 // Symbols of the quarter plane [i0, i0 + 4*NW) as words (4 symbols each).
 template <int NW>
@@ -57,7 +68,100 @@ __device__ __forceinline__ void smem_plane_words(const uint8_t* plane, uint32_t 
   for (int i = 0; i < NW; i++) out[i] = *reinterpret_cast<const uint32_t*>(plane + i0 + 4 * i);
 }
 
-// One symbol; `rem` counts the bits left above the segment's lower bound.
+// Window over a bitstream that lies in shared memory (byte offsets from the buffer start).  Same 64-bit
+// container and word-granular refill as BitWindow, without the ring.
+struct SmemWindow {
+  uint64_t cont;
+  int32_t s;          // 53 - bits consumed from the top of `cont`
+  uint32_t next;      // the word below the container
+  uint32_t rd;        // byte offset of the word the next refill reads
+  uint32_t base_s;    // shared address of the buffer
+};
+__device__ __forceinline__ void swin_seek(SmemWindow& b, uint32_t mark) {  // next unread bit = mark - 1
+  const uint32_t top_byte = (mark - 1) >> 3;
+  const uint32_t q = (top_byte & ~3u) - 4u;
+  b.s = 53 - (int32_t)(8u * (q + 8u) - mark);
+  b.cont = ((uint64_t)lds_u32(b.base_s + q + 4u) << 32) | lds_u32(b.base_s + q);
+  b.next = lds_u32(b.base_s + q - 4u);
+  b.rd = q - 8u;
+}
+__device__ __forceinline__ void swin_refill(SmemWindow& b) {
+  if (b.s <= 21) {
+    b.cont = (b.cont << 32) | b.next;
+    b.s += 32;
+    b.next = lds_u32(b.base_s + b.rd);
+    b.rd -= 4u;
+  }
+}
+__device__ __forceinline__ uint32_t swin_decode(SmemWindow& b, const LutFull& lut, int32_t& rem) {
+  const uint32_t x = (uint32_t)(b.cont >> b.s);
+  const int32_t e = lut.get(x);
+  b.s += e >> 8;
+  rem += e >> 8;
+  return (uint32_t)e;
+}
+// Decode from bit offset `from` down to the first code boundary at or below `bound`.  -> symbols seen.
+__device__ __forceinline__ uint32_t swin_scan(SmemWindow& b, const LutFull& lut, uint32_t from, uint32_t bound, uint32_t& stop) {
+  int32_t rem = (int32_t)(from - bound);
+  uint32_t n = 0;
+  if (rem > 0) {
+    swin_seek(b, from);
+    for (;;) {
+      swin_refill(b);
+      swin_decode(b, lut, rem);
+      n++;
+      if (rem <= 0) break;
+      swin_decode(b, lut, rem);
+      n++;
+      if (rem <= 0) break;
+    }
+  }
+  stop = (uint32_t)((int32_t)bound + rem);
+  return n;
+}
+// Whole words where the thread owns all four bytes, single bytes at its two ends.
+struct PlaneWriter {
+  uint8_t* plane;
+  uint32_t off, pos, acc;
+  __device__ __forceinline__ PlaneWriter(uint8_t* p, uint32_t o) : plane(p), off(o), pos(o), acc(0) {}
+  __device__ __forceinline__ void put(uint32_t sym) {
+    acc |= sym << ((pos & 3u) * 8u);
+    pos++;
+    if ((pos & 3u) == 0) {
+      if (pos - 4 >= off) {
+        *reinterpret_cast<uint32_t*>(plane + pos - 4) = acc;
+      } else {
+        for (uint32_t q = off; q < pos; q++) plane[q] = (uint8_t)(acc >> ((q & 3u) * 8u));
+      }
+      acc = 0;
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (pos & 3u) {
+      const uint32_t w0 = pos & ~3u;
+      for (uint32_t q = (w0 > off ? w0 : off); q < pos; q++) plane[q] = (uint8_t)(acc >> ((q & 3u) * 8u));
+    }
+  }
+};
+__device__ __forceinline__ void swin_emit(SmemWindow& b, const LutFull& lut, uint32_t from, uint32_t n, uint8_t* plane, uint32_t off) {
+  if (n == 0) return;
+  swin_seek(b, from);
+  int32_t dummy = 0;
+  PlaneWriter w(plane, off);
+  uint32_t i = 0;
+  for (; i + 2 <= n; i += 2) {
+    swin_refill(b);
+    w.put(swin_decode(b, lut, dummy) & 0xFFu);
+    w.put(swin_decode(b, lut, dummy) & 0xFFu);
+  }
+  if (i < n) {
+    swin_refill(b);
+    w.put(swin_decode(b, lut, dummy) & 0xFFu);
+  }
+  w.finish();
+}
+
+// ---- fallback: the stream stays in global memory, each thread feeds a private ring (decode.cuh) ----
 template <class LUT>
 __device__ __forceinline__ uint32_t sync_decode(BitWindow& b, const LUT& lut, int32_t& rem) {
   const uint32_t x = (uint32_t)(b.cont >> b.s);
@@ -66,9 +170,6 @@ __device__ __forceinline__ uint32_t sync_decode(BitWindow& b, const LUT& lut, in
   rem += e >> 8;
   return (uint32_t)e;
 }
-
-// Decode from bit offset `from` down to the first code boundary at or below `bound`.
-// -> symbols seen; `stop` = that boundary.
 __device__ __forceinline__ uint32_t sync_scan(BitWindow& b, const LutFull& lut, uint32_t from, uint32_t bound, uint32_t& stop) {
   int32_t rem = (int32_t)(from - bound);
   uint32_t n = 0;
@@ -99,42 +200,70 @@ __device__ __forceinline__ uint32_t sync_scan(BitWindow& b, const LutFull& lut, 
   stop = (uint32_t)((int32_t)bound + rem);
   return n;
 }
-
-// Decode exactly `n` symbols from bit offset `from` into plane[off ..): whole words where the
-// thread owns all four bytes, single bytes at its two ends.
 __device__ __forceinline__ void sync_emit(BitWindow& b, const LutFull& lut, uint32_t from, uint32_t n, uint8_t* plane, uint32_t off) {
   if (n == 0) return;
   window_seek(b, from);
   int32_t dummy = 0;
-  uint32_t pos = off, acc = 0;
+  PlaneWriter w(plane, off);
   const uint32_t end = off + n;
-  while (pos < end) {
+  while (w.pos < end) {
     ring_top_up(b, 1);
     cp_async_commit();
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      if (pos < end) {
+      if (w.pos < end) {
         if ((k & 1) == 0) window_refill(b);
-        const uint32_t sym = sync_decode(b, lut, dummy) & 0xFFu;
-        acc |= sym << ((pos & 3u) * 8u);
-        pos++;
-        if ((pos & 3u) == 0) {
-          if (pos - 4 >= off) {
-            *reinterpret_cast<uint32_t*>(plane + pos - 4) = acc;
-          } else {
-            for (uint32_t q = off; q < pos; q++) plane[q] = (uint8_t)(acc >> ((q & 3u) * 8u));
-          }
-          acc = 0;
-        }
+        w.put(sync_decode(b, lut, dummy) & 0xFFu);
       }
     }
     cp_async_wait<1>();
   }
   cp_async_wait<0>();
-  if (pos & 3u) {
-    const uint32_t w0 = pos & ~3u;
-    for (uint32_t q = (w0 > off ? w0 : off); q < pos; q++) plane[q] = (uint8_t)(acc >> ((q & 3u) * 8u));
+  w.finish();
+}
+
+// ====================================================================================
+// Table descriptions of all coded items, one warp per item (lane 0 runs the <= 255 serial tANS
+// steps of entropy_common.c:41-215 once per ITEM; the four bitstream CTAs of the item read the result).
+// ====================================================================================
+constexpr int kParseWarps = 4;
+constexpr uint32_t kParseHdrMax = 272;   // a table description is at most 1 + 255 bytes (huf_compress.c:140-167); + slack for the 4-byte peeks
+struct ParseSmem {
+  FseDec D;
+  __align__(16) uint8_t hdr[kParseHdrMax];
+  uint8_t weights[256];
+};
+// All 32 lanes call: the warp copies the item's first bytes into shared memory (the serial parser reads them a
+// byte at a time), lane 0 parses, the warp writes the result out.
+__device__ __forceinline__ void parse_item(const DecodeCfg& cfg, uint32_t hi, ParseSmem& P) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t item = cfg.hlist[hi];
+  const ItemDesc d = cfg.items[item];
+  ItemTable& T = cfg.tables[hi];
+  const uint32_t take = d.src_len < kParseHdrMax ? d.src_len : kParseHdrMax;
+  for (uint32_t i = lane; i < take; i += 32) P.hdr[i] = cfg.body[d.src_off + i];
+  __syncwarp();
+  int nsym = 0, lg = 0, hsize = -1;
+  if (lane == 0) {
+    hsize = huf_read_weights(P.weights, &nsym, &lg, P.hdr, take, P.D);
+    if (hsize >= 0 && lg > kDecLutLog) {
+      atomicOr(&cfg.ctrl->error, kErrUnsupported);
+      hsize = -1;
+    } else if (hsize < 0) {
+      atomicOr(&cfg.ctrl->error, kErrCorrupt);
+    }
+    T.hsize = hsize;
+    T.lg = lg;
+    T.nsym = nsym;
   }
+  __syncwarp();
+  reinterpret_cast<uint2*>(T.weights)[lane] = reinterpret_cast<const uint2*>(P.weights)[lane];
+}
+__global__ void __launch_bounds__(kParseWarps * 32) k_parse_tables(DecodeCfg cfg) {
+  __shared__ ParseSmem P[kParseWarps];
+  const uint32_t nh = cfg.ctrl->huf_count;
+  const uint32_t w = blockIdx.x * kParseWarps + (threadIdx.x >> 5);
+  if (w < nh) parse_item(cfg, w, P[threadIdx.x >> 5]);
 }
 
 // items: hlist[0 .. ctrl->huf_count) = coded items (g * K + c) of chunks in fused or general mode.
@@ -152,25 +281,13 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
     const ItemDesc d = cfg.items[item];
     const uint32_t mode = cfg.mode[c];
 
-    // ---- table description -> weights (one thread; <= 255 serial tANS steps) ----
-    if (tid == 0) {
-      int nsym = 0, lg = 0;
-      FseDec& D = *reinterpret_cast<FseDec*>(S.plane);
-      int hsize = huf_read_weights(S.weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
-      if (hsize >= 0 && lg > kDecLutLog) {
-        atomicOr(&cfg.ctrl->error, kErrUnsupported);
-        hsize = -1;
-      } else if (hsize < 0) {
-        atomicOr(&cfg.ctrl->error, kErrCorrupt);
-      }
-      S.hsize = hsize;
-      S.nsym = nsym;
-      S.lg = lg;
-      for (int w = 0; w < kHufLogMax + 2; w++) S.cls_count[w] = 0;
-    }
+    // ---- table description: parsed once per item by k_parse_tables ----
+    const ItemTable& T = cfg.tables[work >> 2];
+    const int hsize = T.hsize, lg = T.lg, nsym = T.nsym;
+    if (hsize < 0) return;  // (uniform; the parse kernel raised the error)
+    if (tid < kHufLogMax + 2) S.cls_count[tid] = 0;
+    S.weights[tid] = T.weights[tid];   // (kSyncThreads == 256)
     __syncthreads();
-    const int hsize = S.hsize, lg = S.lg, nsym = S.nsym;
-    if (hsize < 0) return;  // (uniform)
     // ---- full table, one thread per symbol (huf_decompress.c:151-183: weights ascending, symbols
     //      ascending within a weight, 2^(w-1) consecutive entries each) ----
     int w_mine = 0;
@@ -234,12 +351,33 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
       if (tid == 0) atomicOr(&cfg.ctrl->error, kErrCorrupt);
       return;  // (uniform: every thread computed the same)
     }
-    __syncthreads();  // table complete
-    BitWindow b;
-    const uint32_t so = window_frame(b, p + s_off, cfg.body, S.ring[tid]);
-    const uint32_t mark = 8u * (so + s_len - 1) + (uint32_t)hb32(lastb);
-    const uint32_t first = b.start_bit;
     const LutFull lut{S.lut, kDecLutLog};
+    const uint8_t* sp = p + s_off;                       // the bitstream: s_len bytes
+    const bool in_smem = s_len <= kSyncStreamCap;        // (uniform)
+    uint32_t mark, first;
+    SmemWindow sw;
+    BitWindow b;
+    if (in_smem) {
+      // aligned 16-byte blocks from kSyncPad bytes below the block that holds the first byte; blocks that would
+      // start in front of the body are skipped (never needed: a stream starts >= 16 bytes into the body)
+      const uintptr_t blk0 = ((uintptr_t)sp & ~(uintptr_t)15) - kSyncPad;
+      const uint32_t head = (uint32_t)((uintptr_t)sp - blk0);               // offset of the stream inside sbuf
+      const uint32_t nblk = (head + s_len + 15u) >> 4;
+      for (uint32_t i = tid; i < nblk; i += kSyncThreads) {
+        const uint8_t* g = reinterpret_cast<const uint8_t*>(blk0) + 16u * i;
+        if (g >= cfg.body - 15) cp_async16(S.sbuf + 16u * i, g);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      sw.base_s = (uint32_t)__cvta_generic_to_shared(S.sbuf);
+      first = 8u * head;
+      mark = 8u * (head + s_len - 1) + (uint32_t)hb32(lastb);
+    } else {
+      const uint32_t so = window_frame(b, sp, cfg.body, S.sbuf + (size_t)tid * kRingBytes);
+      mark = 8u * (so + s_len - 1) + (uint32_t)hb32(lastb);
+      first = b.start_bit;
+    }
+    __syncthreads();  // table and stream complete
     // ---- segments ----
     const uint32_t bits = mark - first;
     uint32_t segbits = (bits + kSyncThreads - 1) / kSyncThreads;
@@ -249,7 +387,7 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
     uint32_t from = top, stop = top, n = 0;
     bool need = true;
     for (int round = 0; round <= kSyncThreads; round++) {
-      if (need) n = sync_scan(b, lut, from, bound, stop);
+      if (need) n = in_smem ? swin_scan(sw, lut, from, bound, stop) : sync_scan(b, lut, from, bound, stop);
       S.stop[tid] = stop;
       __syncthreads();
       const uint32_t nf = tid ? S.stop[tid - 1] : mark;
@@ -278,7 +416,8 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
       if (tid == 0) atomicOr(&cfg.ctrl->error, kErrCorrupt);
       return;  // (uniform)
     }
-    sync_emit(b, lut, from, n, S.plane, off);
+    if (in_smem) swin_emit(sw, lut, from, n, S.plane, off);
+    else sync_emit(b, lut, from, n, S.plane, off);
     __syncthreads();
     // ---- quarter plane -> elements, or -> the chunk's workspace plane ----
     if (mode == kModeFused) {
@@ -370,6 +509,18 @@ __global__ void __launch_bounds__(kSyncThreads) k_huf_decode_sync_batch(BatchCfg
     else if (cfg.G == 2) sync_process<2>(cfg, cfg.out, S, work);
     else sync_process<4>(cfg, cfg.out, S, work);
   }
+}
+
+// one warp per coded item of every tensor of a batch (flat index over item_start / 4)
+__global__ void __launch_bounds__(kParseWarps * 32) k_parse_tables_batch(BatchCfg B) {
+  __shared__ ParseSmem P[kParseWarps];
+  const uint64_t total = B.item_start[B.n] >> 2;
+  const uint64_t w = (uint64_t)blockIdx.x * kParseWarps + (threadIdx.x >> 5);
+  if (w >= total) return;
+  const uint32_t t = batch_find(B.item_start, B.n, 4 * w);
+  const DecodeCfg& cfg = B.cfgs[t];
+  const uint64_t hi = w - (B.item_start[t] >> 2);
+  if (hi < cfg.ctrl->huf_count) parse_item(cfg, (uint32_t)hi, P[threadIdx.x >> 5]);
 }
 
 }  // namespace zb

@@ -47,9 +47,9 @@ inline bool cuda_ok(cudaError_t e) {
 // Off by default.  bench.py turns it on to attribute the step time to kernels; the events
 // sit between launches on the same stream, so they do not change the schedule.
 enum KernelId { kKDecodeMeta = 0, kKHufDecode, kKHufDecodePlanar, kKRegroup, kKEncodeStats, kKEncodeTable, kKEncodeScan, kKEncodeWrite, kKEncodeWriteRagged, kKSplit,
-                kKRegroupPlanar, kKDecodeOverflow, kKHufDecodeSync, kKCount };
+                kKRegroupPlanar, kKDecodeOverflow, kKHufDecodeSync, kKParseTables, kKCount };
 const char* const kKernelNames[kKCount] = {"k_decode_meta", "k_huf_decode_fused", "k_huf_decode_planar", "k_regroup", "k_encode_hist", "k_encode_table",
-                                           "k_encode_scan", "k_encode_write_warp", "k_encode_write_ragged", "k_split_planar", "k_regroup_planar", "k_decode_overflow", "k_huf_decode_sync"};
+                                           "k_encode_scan", "k_encode_write_warp", "k_encode_write_ragged", "k_split_planar", "k_regroup_planar", "k_decode_overflow", "k_huf_decode_sync", "k_parse_tables"};
 struct TimedSpan {
   int id;
   cudaEvent_t a, b;
@@ -177,10 +177,11 @@ inline uint64_t num_chunks(size_t n, size_t chunk) { return (n + chunk - 1) / ch
 // workspace.  The "full" size gives every chunk a pool slot (faster for streams that are all
 // general chunks, e.g. fp32 tensors upcast from bf16).
 constexpr uint64_t kDefaultSlots = 64;
-constexpr uint64_t kSyncDefaultMaxChunks = 2048;  // measured crossover with the one-thread-per-bitstream kernels: 256 MiB 0.78 vs 1.5 ms,
-                                                  // 1 GiB 2.5 vs 1.5 ms (profiles/r2_sweep_1gpu.jsonl)
+constexpr uint64_t kSyncTablesMaxChunks = 16384;  // largest tensor the sync decoder can be asked to take (ZIPNN_B200_SYNC_MAX is clamped to it)
+constexpr uint64_t kSyncDefaultMaxChunks = 3072;  // measured crossover with the one-thread-per-bitstream kernels: 256 MiB 0.52 vs 1.5 ms,
+                                                  // 1 GiB 2.0 vs 1.55 ms (profiles/r2_kernel_times.jsonl)
 struct DecWs {
-  size_t items_off, mode_off, slot_off, rlist_off, olist_off, hlist_off, fill_off, planes_off, pstride, fixed;
+  size_t items_off, mode_off, slot_off, rlist_off, olist_off, hlist_off, tables_off, fill_off, planes_off, pstride, fixed;
 };
 inline DecWs dec_ws_layout(size_t orig, int G, size_t chunk) {
   DecWs L;
@@ -191,7 +192,9 @@ inline DecWs dec_ws_layout(size_t orig, int G, size_t chunk) {
   L.rlist_off = round_up(L.slot_off + 4 * K, 256);
   L.olist_off = round_up(L.rlist_off + 4 * K, 256);
   L.hlist_off = round_up(L.olist_off + 4 * K, 256);
-  L.fill_off = round_up(L.hlist_off + 4 * (size_t)G * K, 256);
+  // parsed table descriptions for the per-bitstream-CTA decoder: only tensors it takes (K <= kSyncTablesMaxChunks)
+  L.tables_off = round_up(L.hlist_off + 4 * (size_t)G * K, 256);
+  L.fill_off = round_up(L.tables_off + (K <= kSyncTablesMaxChunks ? sizeof(ItemTable) * (size_t)G * K : 0), 256);
   L.planes_off = round_up(L.fill_off + (size_t)kFillBytes * G * K, 256);
   L.pstride = round_up(chunk / (size_t)G, 16) + 16;
   L.fixed = L.planes_off + 256;
@@ -332,11 +335,12 @@ static int fill_decode_cfg(DecodeCfg& cfg, const void* d_body, size_t body_len, 
     cfg.ovf_slots = 0;
   }
   cfg.hlist = use_sync ? (uint32_t*)(ws + L.hlist_off) : nullptr;
+  cfg.tables = (ItemTable*)(ws + L.tables_off);
   return ZIPNN_B200_OK;
 }
 static uint64_t sync_max_chunks() {
   const Knobs kn = knobs();
-  return kn.sync_max >= 0 ? (uint64_t)kn.sync_max : kSyncDefaultMaxChunks;
+  return std::min<uint64_t>(kn.sync_max >= 0 ? (uint64_t)kn.sync_max : kSyncDefaultMaxChunks, kSyncTablesMaxChunks);
 }
 
 int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int bits_mode, int bytes_mode,
@@ -383,6 +387,11 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
         return v;
       }();
       const unsigned grid = (unsigned)std::min<uint64_t>(4 * nitems, (uint64_t)nb * sm_count_cached());
+      {
+        ScopedTimer tp(kKParseTables, st);
+        k_parse_tables<<<(unsigned)((nitems + kParseWarps - 1) / kParseWarps), kParseWarps * 32, 0, st>>>(cfg);
+        ZB_LAUNCHED();
+      }
       ScopedTimer tm(kKHufDecodeSync, st);
       k_huf_decode_sync<GG><<<grid, kSyncThreads, sizeof(SyncShared), st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
@@ -586,6 +595,11 @@ int zipnn_b200_decompress_batch(const zipnn_b200_batch_item* items, int n, void*
         return v;
       }();
       const unsigned grid = (unsigned)std::min<uint64_t>(item_start[n], (uint64_t)nb * sms);
+      {
+        ScopedTimer tp(kKParseTables, st);
+        k_parse_tables_batch<<<(unsigned)(((item_start[n] >> 2) + kParseWarps - 1) / kParseWarps), kParseWarps * 32, 0, st>>>(B);
+        ZB_LAUNCHED();
+      }
       ScopedTimer tm(kKHufDecodeSync, st);
       k_huf_decode_sync_batch<<<grid, kSyncThreads, sizeof(SyncShared), st>>>(B);
       ZB_LAUNCHED();

@@ -77,6 +77,24 @@ def _bytes_tensor(b: bytes, device) -> torch.Tensor:
     return torch.frombuffer(bytearray(b), dtype=torch.uint8).to(device)
 
 
+def _ipc_alias(t: Optional[torch.Tensor], src: int, group=None) -> torch.Tensor:
+    """Every rank gets a tensor that ALIASES rank `src`'s CUDA tensor `t` (CUDA IPC: the ranks are processes on
+    one node).  Copies to / from it are peer copies over NVLink, issued by the rank that owns the other side --
+    no send/recv pairing, no staging through NCCL's channel buffers."""
+    from torch.multiprocessing.reductions import reduce_tensor
+    rank = dist.get_rank(group)
+    box = [reduce_tensor(t) if rank == src else None]
+    dist.broadcast_object_list(box, src, group=group)
+    if rank == src:
+        return t
+    fn, args = box[0]
+    return fn(*args)
+
+
+def _use_ipc(t: torch.Tensor, transport: str) -> bool:
+    return transport == "ipc" or (transport == "auto" and t.is_cuda and dist.get_backend() == "nccl")
+
+
 def _p2p(ops):
     if ops:
         for w in dist.batch_isend_irecv(ops):
@@ -85,7 +103,8 @@ def _p2p(ops):
 
 # ----------------------------------------------------------------------------------------------
 def gather_stream(local_stream: torch.Tensor, local_hdr_len: int, G: int, K_local: int, n_local: int,
-                  global_header: bytes, dst: int = 0, group=None, chunk: Optional[int] = None) -> Optional[torch.Tensor]:
+                  global_header: bytes, dst: int = 0, group=None, chunk: Optional[int] = None,
+                  transport: str = "auto", cache: Optional[dict] = None) -> Optional[torch.Tensor]:
     """Merge per-rank streams (each covering a contiguous chunk range, in rank order) into the
     single stream the reference would have produced for the concatenated input.
 
@@ -129,6 +148,41 @@ def gather_stream(local_stream: torch.Tensor, local_hdr_len: int, G: int, K_loca
     cum_rows = m.cum.astype(np.int64) + np.array(rank_base[rank], dtype=np.int64).reshape(G, 1)
     cum_rows = torch.from_numpy(cum_rows).to(dev)
 
+    if _use_ipc(ls, transport):
+        # ---- peer copies: every rank writes its rows and payload slices straight into the owner's buffer ----
+        # The owner's buffer and the other ranks' aliases of it are kept between calls (`cache`): sharing a fresh
+        # allocation costs a pickled handle broadcast and an IPC open per rank, a few ms each.
+        if cache is not None and cache.get("cap", 0) >= total and cache.get("dst") == dst:
+            view = cache["view"]
+        else:
+            cap = total + (total >> 3) if cache is not None else total
+            buf = torch.empty(cap, dtype=torch.uint8, device=dev) if rank == dst else None
+            view = _ipc_alias(buf, dst, group)
+            if cache is not None:
+                cache.clear()
+                cache.update(cap=cap, dst=dst, view=view)
+        out = view[:total] if rank == dst else None
+        if rank == dst:
+            hdr = bytearray(global_header)
+            hdr[16:24] = int(sum(ns)).to_bytes(8, "little")
+            hdr[24:32] = int(total).to_bytes(8, "little")
+            view[:H] = _bytes_tensor(bytes(hdr), dev)
+        if K_local:
+            c0 = c_off[rank]
+            cum_bytes = cum_rows.contiguous().view(torch.uint8).view(G, 8 * K_local)
+            for g in range(G):
+                view[H + g * K + c0: H + g * K + c0 + K_local].copy_(types_rows[g], non_blocking=True)
+                a = H + G * K + 8 * (g * K + c0)
+                view[a: a + 8 * K_local].copy_(cum_bytes[g], non_blocking=True)
+                if tot[rank][g]:
+                    a = group_base[g] + rank_base[rank][g]
+                    src0 = m.payload0 + m.base[g]
+                    view[a: a + tot[rank][g]].copy_(ls[src0: src0 + tot[rank][g]], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        if rank != dst and cache is None:
+            del view
+        dist.barrier(group=group)
+        return out
     if rank == dst:
         out = torch.empty(total, dtype=torch.uint8, device=dev)
         hdr = bytearray(global_header)
@@ -176,7 +230,7 @@ def gather_stream(local_stream: torch.Tensor, local_hdr_len: int, G: int, K_loca
 
 
 def scatter_stream(stream: Optional[torch.Tensor], hdr_len: int, G: int, chunk: int, src: int = 0, group=None,
-                   device=None) -> Tuple[torch.Tensor, int, bytes]:
+                   device=None, transport: str = "auto") -> Tuple[torch.Tensor, int, bytes]:
     """Inverse of gather_stream.  The owner (`src`) holds the whole stream; every rank gets back
     (local_stream, local_orig_bytes, global_header) where local_stream is a self-contained
     stream -- 32-byte header, its rows of the tables, its payload -- for its chunk range."""
@@ -222,6 +276,20 @@ def scatter_stream(stream: Optional[torch.Tensor], hdr_len: int, G: int, chunk: 
         local[HEADER_LEN: HEADER_LEN + G * Kl] = torch.from_numpy(np.ascontiguousarray(meta.types[:, c0:c1]).reshape(-1)).to(dev)
         rebased = meta.cum[:, c0:c1].astype(np.int64) - np.array([int(meta.cum[g, c0 - 1]) if c0 else 0 for g in range(G)], dtype=np.int64).reshape(G, 1)
         local[HEADER_LEN + G * Kl: HEADER_LEN + 9 * G * Kl] = torch.from_numpy(np.ascontiguousarray(rebased).reshape(-1)).to(dev).view(torch.uint8)
+    if _use_ipc(local, transport):
+        # ---- peer copies: every rank pulls its payload ranges out of the owner's stream ----
+        view = _ipc_alias(s if rank == src else None, src, group)
+        at = HEADER_LEN + 9 * G * Kl
+        for g in range(G):
+            off, ln = span(rank, g)
+            if ln:
+                local[at: at + ln].copy_(view[off: off + ln], non_blocking=True)
+            at += ln
+        torch.cuda.current_stream(dev).synchronize()
+        if rank != src:
+            del view
+        dist.barrier(group=group)
+        return local, n_local, gheader
     # payload: point-to-point from the owner, each piece straight into place
     ops = []
     at = HEADER_LEN + 9 * G * Kl
@@ -263,6 +331,8 @@ class ShardedZipNN:
         self._ZipNN = ZipNN
         self._compress_local = compress_local
         self._decompress_local = decompress_local
+        self._gather_cache = {}   # owner buffer + aliases, reused while it is large enough (the returned stream is a
+                                  # view of it: valid until the next compress / gather of this object)
 
     def _codec(self):
         if self._compress_local is None:
@@ -291,9 +361,17 @@ class ShardedZipNN:
             cnt = torch.tensor([local.numel()], dtype=torch.int64, device=stream.device)
             dist.all_reduce(cnt, group=self.group)
             global_shape = (int(cnt.item()),)
-        ext = zipnn_pack_shape(tuple(global_shape)) if self.kw.get("input_format", "torch") != "byte" else b""
         assert world >= 1
-        return gather_stream(stream, HEADER_LEN, plan["num_buf"], K_local, n_local, bytes(gh) + ext, dst, self.group, chunk=plan["chunk"])
+        return self.gather(stream, plan, n_local, global_shape, dst)
+
+    def gather(self, local_stream: torch.Tensor, plan: dict, n_local: int, global_shape, dst: int = 0) -> Optional[torch.Tensor]:
+        """The exchange half of `compress`: per-rank streams -> the single-GPU stream on `dst`."""
+        from .util_torch import zipnn_pack_shape
+        K_local = (n_local + plan["chunk"] - 1) // plan["chunk"]
+        gh = bytearray(plan["header"][:HEADER_LEN])
+        ext = zipnn_pack_shape(tuple(global_shape)) if self.kw.get("input_format", "torch") != "byte" else b""
+        return gather_stream(local_stream, HEADER_LEN, plan["num_buf"], K_local, n_local, bytes(gh) + ext, dst, self.group,
+                             chunk=plan["chunk"], cache=self._gather_cache)
 
     def decompress(self, stream: Optional[torch.Tensor], src: int = 0, device=None) -> torch.Tensor:
         from .util_torch import torch_dtype_of_code, zipnn_unpack_shape
