@@ -607,7 +607,8 @@ def run_ours(args, rank, local_rank, world):
     dom_ms = per_launch[dom][0]
     achieved = algo.get(dom, N) / (dom_ms * 1e-3) / 1e9
     kernels = {k: {"ms_per_launch": round(v[0], 4), "launches": v[1],
-                   "algo_gbs": round(algo[k] / (v[0] * 1e-3) / 1e9, 1) if k in algo and v[0] > 0 else None}
+                   "algo_gbs": round(algo[k] / (v[0] * 1e-3) / 1e9, 1) if k in algo and v[0] > 0 else None,
+                   "roofline_frac": round(algo[k] / (v[0] * 1e-3) / 1e9 / peak, 4) if k in algo and v[0] > 0 else None}
                for k, v in per_launch.items()}
     # DRAM bytes per launch of the dominant kernel: recorded from one `ncu --set full` capture of the same
     # workload (never measured under this run: ncu serialises and replays kernels); null when the

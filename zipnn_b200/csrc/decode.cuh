@@ -262,7 +262,7 @@ constexpr uint32_t kRingBytes = 64;
 
 struct DecodeSmem {
   uint16_t lut[kDecItemsPerWarp][kDecLutEntries];  // also scratch for the table parse
-  __align__(16) uint8_t ring[32][kRingBytes];      // per lane; weights[8][256] alias it during the parse
+  __align__(64) uint8_t ring[32][kRingBytes];      // per lane; weights[8][256] alias it during the parse
 };
 static_assert(sizeof(FseDec) <= sizeof(uint16_t) * kDecLutEntries, "FseDec must fit in one LUT slot");
 static_assert(32 * kRingBytes >= kDecItemsPerWarp * 256, "weights alias the ring");
@@ -270,6 +270,9 @@ static_assert(32 * kRingBytes >= kDecItemsPerWarp * 256, "weights alias the ring
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global" ZB_CPASYNC_L2 " [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global" ZB_CPASYNC_L2 " [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -311,7 +314,7 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
     // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above q = qm + 8
     // (the container and `next` are in registers; later reads are at q - 8 and below)
     if (b.fetch >= 16 + b.floor_off && f + (kRingBytes - 8) >= b.qm) {
-      cp_async16(const_cast<uint8_t*>(b.ring) + (f & (kRingBytes - 1)), b.gbase + f);
+      cp_async16_s(b.ring_s | (f & (kRingBytes - 16)), b.gbase + f);  // f is a multiple of 16; the ring is ring-size aligned
       b.fetch = f;
     }
   }
@@ -323,12 +326,22 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   return v;
 }
 __device__ __forceinline__ void window_refill(BitWindow& b) {
-  if (b.s <= 21) {  // 32 or more bits consumed
-    b.cont = (b.cont << 32) | b.next;
-    b.s += 32;
-    b.next = lds_u32(b.ring_s | (b.qm & (kRingBytes - 4u)));
-    b.qm -= 4u;
-  }
+  // if (s <= 21) { cont = cont << 32 | next; s += 32; next = ring[qm & 60]; qm -= 4; }  -- 32 or more bits consumed.
+  // Written out as predicated PTX: the C++ form loads into a temporary and moves it (one more instruction per
+  // refill), and the kernel's time follows the number of instructions issued per symbol.
+  uint32_t lo = (uint32_t)b.cont, hi = (uint32_t)(b.cont >> 32);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 a;\n\t"
+      "setp.le.s32 p, %0, 21;\n\t"
+      "lop3.b32 a, %4, %6, %5, 0xEA;\n\t"  // (qm & (ring - 4)) | ring_s
+      "@p mov.b32 %2, %1;\n\t"
+      "@p mov.b32 %1, %3;\n\t"
+      "@p add.s32 %0, %0, 32;\n\t"
+      "@p ld.shared.u32 %3, [a];\n\t"
+      "@p add.u32 %4, %4, -4;\n\t}"
+      : "+r"(b.s), "+r"(lo), "+r"(hi), "+r"(b.next), "+r"(b.qm)
+      : "r"(b.ring_s), "n"(kRingBytes - 4));
+  b.cont = ((uint64_t)hi << 32) | lo;
 }
 
 // Frame of reference of a stream at `s`: offsets are taken from a 64-byte aligned address one ring
@@ -399,10 +412,19 @@ struct LutTwo {
                     // the compiler rebuild the shared window base for every lookup)
   uint32_t x_long;
   __device__ __forceinline__ int32_t get(uint32_t x) const {
-    const uint32_t idx = x & 0x7FFu;
-    const uint32_t a_prim = ((x >> 2) & 0x1FEu) | prim_s;  // 2 * (top 8 of the 11 bits); every primary is 512-byte aligned
-    const uint32_t a_tail = tail_s + idx + idx;
-    return lds_s16(idx < x_long ? a_tail : a_prim);      // one load, address selected (see LutCol)
+    // idx < x_long ? tail_s + 2 * idx : ((x >> 2) & 0x1FE) | prim_s -- one load, address selected (see LutCol for
+    // why this is PTX); every primary is 512-byte aligned
+    int32_t v;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 i, a;\n\t"
+        "and.b32 i, %1, 0x7FF;\n\t"
+        "shr.u32 a, %1, 2;\n\t"
+        "lop3.b32 a, a, 0x1FE, %2, 0xEA;\n\t"
+        "setp.lt.u32 p, i, %4;\n\t"
+        "@p mad.lo.u32 a, i, 2, %3;\n\t"
+        "ld.shared.s16 %0, [a];\n\t}"
+        : "=r"(v)
+        : "r"(x), "r"(prim_s), "r"(tail_s), "r"(x_long));
+    return v;
   }
 };
 
@@ -421,17 +443,29 @@ struct LutCol {
   uint32_t tail_s;
   uint32_t x_long;
   __device__ __forceinline__ int32_t get(uint32_t x) const {
-    const uint32_t idx = x & 0x7FFu;
-    // ONE load per symbol: the address is SELECTED between the lane's column and the chunk's tail.  The
-    // kernel is bound by the number of LSU instructions it issues (~2.6 cycles each per SM, whatever their
-    // width, conflicts or predicate: removing the tail lookup altogether -- wrong, timing only -- gave
-    // 8.76 -> 7.44 ms), not by ALU work or by the length of the dependent chain, so one more SEL in front
-    // of the load is cheaper than a second, predicated, load behind it.
-    const uint32_t a_col = (x & 0x7C0u) | col_s;
-    const uint32_t a_tail = tail_s + idx + idx;
-    return lds_s16(idx < x_long ? a_tail : a_col);
+    // ONE load per symbol: the address is SELECTED between the lane's column and the chunk's tail
+    // (idx < x_long ? tail_s + 2 * idx : (x & 0x7C0) | col_s).  Written as PTX because the compiler turns the C++
+    // form into five instructions (idx, x + x, & 0xFFE, compare, predicated add) where three do (idx, compare,
+    // predicated multiply-add); removing the tail lookup altogether -- wrong, timing only -- gave 8.76 -> 7.44 ms,
+    // so each instruction here is ~1.5 % of the kernel.
+    int32_t v;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 i, a;\n\t"
+        "and.b32 i, %1, 0x7FF;\n\t"
+        "lop3.b32 a, %1, 0x7C0, %2, 0xEA;\n\t"
+        "setp.lt.u32 p, i, %4;\n\t"
+        "@p mad.lo.u32 a, i, 2, %3;\n\t"
+        "ld.shared.s16 %0, [a];\n\t}"
+        : "=r"(v)
+        : "r"(x), "r"(col_s), "r"(tail_s), "r"(x_long));
+    return v;
   }
 };
+
+// What a table entry of the fused kernel stores for symbol n.  When the top plane is the exponent plane of a
+// rotated type the symbol is stored rotated right by one bit: the un-rotation of an element,
+// hi' = sign | exp >> 1, lo' = exp << 7 | mant7, then needs no shift at all -- with E = ror8(exp) it is two
+// bit selects per four elements, hi' = (E & 0x7F) | (sm & 0x80), lo' = (E & 0x80) | (sm & 0x7F).
+__device__ __forceinline__ uint32_t lut_symbol(uint32_t n, bool pre_rot) { return pre_rot ? ((n >> 1) | ((n & 1u) << 7)) : n; }
 
 // Tail size for a PB-bit primary: index bound of the codes longer than PB bits (or -1).
 __device__ __forceinline__ int lut_tail_size(const uint8_t* weights, int nsym, int lg, int pb) {
@@ -451,7 +485,7 @@ __device__ __forceinline__ int lut_tail_size(const uint8_t* weights, int nsym, i
 // Fill one lane's column (all 4 lanes of a chunk run it) and, when `with_tail`, the chunk's tail.
 template <int PB>
 __device__ __forceinline__ void fill_lut_col(uint16_t* col /* entry k at col[32 * k] */, uint16_t* tail, bool with_tail,
-                                             const uint8_t* weights, int nsym, int lg) {
+                                             const uint8_t* weights, int nsym, int lg, bool pre_rot) {
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
   for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
@@ -469,7 +503,7 @@ __device__ __forceinline__ void fill_lut_col(uint16_t* col /* entry k at col[32 
     if (w == 0) continue;
     const int len = lg + 1 - w;
     const uint32_t span = 1u << (kDecLutLog - len);
-    const uint32_t e = (uint32_t)n | (((256u - (uint32_t)len) & 0xFFu) << 8);  // symbol | -length
+    const uint32_t e = lut_symbol((uint32_t)n, pre_rot) | (((256u - (uint32_t)len) & 0xFFu) << 8);  // symbol | -length
     const uint32_t u = start[w];
     start[w] = u + span;
     if (len > PB) {
@@ -575,7 +609,7 @@ __device__ __forceinline__ int lut2_tail_size(const uint8_t* weights, int nsym, 
 }
 
 // Step 2: fill the 256-entry primary and the x_long-entry tail.
-__device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const uint8_t* weights, int nsym, int lg) {
+__device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const uint8_t* weights, int nsym, int lg, bool pre_rot) {
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
   for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
@@ -593,7 +627,7 @@ __device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const 
     if (w == 0) continue;
     const int len = lg + 1 - w;
     const uint32_t span = 1u << (kDecLutLog - len);
-    const uint16_t e = (uint16_t)(n | (((256 - len) & 0xFF) << 8));  // symbol | -length
+    const uint16_t e = (uint16_t)(lut_symbol((uint32_t)n, pre_rot) | (uint32_t)(((256 - len) & 0xFF) << 8));  // symbol | -length
     const uint32_t u = start[w];
     start[w] = u + span;
     if (len > 8) {
@@ -877,9 +911,6 @@ struct SidePlane {
 // prefetch only shortened the wait.  cp.async has no destination register: block k+3 is requested
 // at the top of iteration k, joins the commit groups of the stream ring, and an LDS picks it up at
 // the end of iteration k+1, after which its slot is free for block k+5: two slots per lane and plane.
-__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global" ZB_CPASYNC_L2 " [%0], [%1], 16;\n" ::"r"(saddr), "l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ uint4 lds_u128(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
@@ -912,6 +943,18 @@ __device__ __forceinline__ void unrotate_planes(uint32_t& lo, uint32_t& hi) {
   hi = (sm & 0x80808080u) | ((e >> 1) & 0x7F7F7F7Fu);
   lo = ((e << 7) & 0x80808080u) | (sm & 0x7F7F7F7Fu);
 }
+// The same with the exponent bytes already rotated right by one (lut_symbol): two bit selects, written as
+// LOP3 because the compiler splits each into two operations.
+__device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m) {  // (a & m) | (b & ~m)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+  return d;
+}
+__device__ __forceinline__ void unrotate_planes_pre(uint32_t& lo, uint32_t& hi) {
+  const uint32_t sm = lo, e = hi;
+  hi = bitselect(sm, e, 0x80808080u);
+  lo = bitselect(e, sm, 0x80808080u);
+}
 
 // Output rows.  A lane produces 16*G bytes per iteration, 64 KiB away from its neighbours'
 // data, so direct stores cost one LSU wavefront per lane.  Instead each lane fills a 128-byte
@@ -933,7 +976,7 @@ __device__ __forceinline__ void emit_elements(uint32_t (&pl)[G][4], bool rot, ui
   }
   if (rot) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) unrotate_planes(pl[(G - 2) % G][q], pl[G - 1][q]);
+    for (int q = 0; q < 4; q++) unrotate_planes_pre(pl[(G - 2) % G][q], pl[G - 1][q]);  // the tables hold ror8(symbol)
   }
   uint32_t w[4 * G];
   if (G == 2) {
@@ -1069,7 +1112,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       }
       if (builder) {
         if (hsize >= 0) {
-          if (PB == 0) fill_lut2(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + 256 * slot, S.tail() + tail_at, weights, nsym, lg);
+          if (PB == 0) fill_lut2(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + 256 * slot, S.tail() + tail_at, weights, nsym, lg, rot);
         } else {
           // Not an error yet: a table that needs the big scratch, a long tail or log 12, or a
           // corrupt one.  Hand the chunk to the general kernels, which decide.
@@ -1084,7 +1127,7 @@ __global__ void __launch_bounds__(32) k_huf_decode_fused(DecodeCfg cfg, uint8_t*
       if (PB != 0) {  // private columns: the 4 lanes of a chunk fill their own copy in parallel
         nsym = __shfl_sync(0xffffffffu, nsym, lane & ~3);
         if (active && hsize >= 0)
-          fill_lut_col<(PB ? PB : 5)>(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + lane, S.tail() + tail_at, stream == 0, weights, nsym, lg);
+          fill_lut_col<(PB ? PB : 5)>(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + lane, S.tail() + tail_at, stream == 0, weights, nsym, lg, rot);
       }
       __syncwarp();  // the ring and the stage (aliased by the parse scratch) are free from here on
     }
