@@ -13,15 +13,13 @@ from zipnn_b200 import ZipNN, _native  # noqa: E402
 
 CONFIGS = [
     {},
-    {"ZIPNN_B200_TMA": "0", "ZIPNN_B200_GRID_MODE": "1"},
-    {"ZIPNN_B200_TMA": "0"},
-    {"ZIPNN_B200_TMA": "0", "ZIPNN_B200_GRID_MODE": "1"},
-    {"ZIPNN_B200_GRID_MODE": "1"},
-    {"ZIPNN_B200_TMA": "0", "ZIPNN_B200_WARPS_PER_SM": "16"},
-    {"ZIPNN_B200_WARPS_PER_SM": "16"},
-    {"ZIPNN_B200_WARPS_PER_SM": "14"},
-    {"ZIPNN_B200_WARPS_PER_SM": "12"},
-    {"ZIPNN_B200_WARPS_PER_SM": "8"},
+    {"ZIPNN_B200_SMEM_PAD": "1024"},    # fewer resident warps per SM (shared memory is what limits them)
+    {"ZIPNN_B200_SMEM_PAD": "3072"},
+    {"ZIPNN_B200_SMEM_PAD": "6144"},
+    {"ZIPNN_B200_SMEM_PAD": "12288"},
+    {"ZIPNN_B200_TMA": "0"},            # side plane through cp.async slots instead of bulk tensor tiles
+    {"ZIPNN_B200_TMA": "1"},            # ... and the output rows by bulk tensor stores
+    {"ZIPNN_B200_GRID_MODE": "0"},      # persistent grid
 ]
 
 

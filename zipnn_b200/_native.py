@@ -63,7 +63,8 @@ def lib() -> C.CDLL:
                     raise ZipNNNativeError(-1, f"libzipnn_b200.so is missing and could not be built: {exc}") from exc
                 import warnings
                 warnings.warn(f"zipnn_b200: libzipnn_b200.so looks older than its sources and could not be rebuilt ({exc}); loading it as is")
-            L = C.CDLL(LIB_PATH)
+            # experiments only: a variant build of the same sources (tools/decode_probe.py)
+            L = C.CDLL(os.environ.get("ZIPNN_B200_LIB_VARIANT") or LIB_PATH)
             vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
             szp = C.POINTER(C.c_size_t)
             sig = {

@@ -40,17 +40,15 @@ constexpr uint32_t kSyncStreamCap = 28u * 1024u;   // bitstream bytes kept in sh
 constexpr uint32_t kSyncPad = 32u;                // readable bytes below the stream's first aligned block
 
 struct SyncShared {
-  uint16_t lut[kDecLutEntries];                    // full table: symbol | (-length << 8), replicated into 11 bits
   // The whole bitstream, copied once by the CTA (aligned 16-byte blocks, so the stream keeps its offset mod 16):
   // every pass of every thread reads it from here -- no per-thread ring, no cp.async, no refill latency on a
   // re-seek.  A stream longer than the buffer (possible in the format, not seen in float tensors) falls back
   // to the per-thread rings of the one-thread-per-bitstream kernels, which alias this buffer.
   __align__(64) uint8_t sbuf[kSyncPad + kSyncStreamCap + 32];
   uint32_t stop[kSyncThreads];                     // bit offset where segment m's decode stopped
-  uint8_t weights[256];
   uint32_t warp_tot[kSyncThreads / 32];
   uint32_t cls_start[kHufLogMax + 2];              // index-space start of weight class w (11-bit space)
-  uint32_t cls_count[kHufLogMax + 2];
+  uint32_t cls_warp[kSyncThreads / 32][16];        // symbols of weight class w in warp q (w <= kHufLogMax = 12)
   PlaneSrc src[4];
   __align__(16) uint8_t plane[kHufBlockMax / 4 + 16];  // the decoded quarter plane
 };
@@ -68,58 +66,114 @@ __device__ __forceinline__ void smem_plane_words(const uint8_t* plane, uint32_t 
   for (int i = 0; i < NW; i++) out[i] = *reinterpret_cast<const uint32_t*>(plane + i0 + 4 * i);
 }
 
+// The CTA's full table (symbol | (-length << 8), replicated into 11 bits) lies on a 4 KiB boundary of the shared
+// address space, so that the address of an entry is ONE operation: (x & 0xFFE) | table address.  The dynamic
+// buffer is only 1 KiB aligned, hence the slack: [pad to 4 KiB][table 4 KiB][SyncShared].
+constexpr size_t kSyncSmemBytes = sizeof(SyncShared) + 4096 + 3072;
+struct SyncCarve {
+  uint16_t* lut;
+  uint32_t lut_s;
+  SyncShared* S;
+};
+__device__ __forceinline__ SyncCarve sync_carve(unsigned char* raw) {
+  const uint32_t base_s = (uint32_t)__cvta_generic_to_shared(raw);
+  const uint32_t off = (4096u - (base_s & 4095u)) & 4095u;
+  SyncCarve c;
+  c.lut = reinterpret_cast<uint16_t*>(raw + off);
+  c.lut_s = base_s + off;
+  c.S = reinterpret_cast<SyncShared*>(raw + off + 4096);
+  return c;
+}
+
 // Window over a bitstream that lies in shared memory (byte offsets from the buffer start).  Same 64-bit
-// container and word-granular refill as BitWindow, without the ring.
+// container and word-granular refill as BitWindow, without the ring.  The shift is kept one lower than
+// BitWindow's (s1 = 52 - bits consumed from the top of `cont`), so that (uint32_t)(cont >> s1) carries the
+// next 11 stream bits in [11:1]: masked with 0xFFE that IS the byte offset of the 16-bit table entry.  s1 is
+// >= 10 at every peek (<= 31 bits are consumed after a refill, <= 42 before the second symbol of a pair).
 struct SmemWindow {
   uint64_t cont;
-  int32_t s;          // 53 - bits consumed from the top of `cont`
+  int32_t s1;
   uint32_t next;      // the word below the container
-  uint32_t rd;        // byte offset of the word the next refill reads
+  uint32_t ra;        // shared address of the word the next refill reads
   uint32_t base_s;    // shared address of the buffer
+  uint32_t lut_s;     // shared address of g_sync_lut (4 KiB aligned)
 };
 __device__ __forceinline__ void swin_seek(SmemWindow& b, uint32_t mark) {  // next unread bit = mark - 1
   const uint32_t top_byte = (mark - 1) >> 3;
   const uint32_t q = (top_byte & ~3u) - 4u;
-  b.s = 53 - (int32_t)(8u * (q + 8u) - mark);
+  b.s1 = 52 - (int32_t)(8u * (q + 8u) - mark);
   b.cont = ((uint64_t)lds_u32(b.base_s + q + 4u) << 32) | lds_u32(b.base_s + q);
   b.next = lds_u32(b.base_s + q - 4u);
-  b.rd = q - 8u;
+  b.ra = b.base_s + q - 8u;
 }
 __device__ __forceinline__ void swin_refill(SmemWindow& b) {
-  if (b.s <= 21) {
-    b.cont = (b.cont << 32) | b.next;
-    b.s += 32;
-    b.next = lds_u32(b.base_s + b.rd);
-    b.rd -= 4u;
-  }
+  // if (s1 <= 20) { cont = cont << 32 | next; s1 += 32; next = *ra; ra -= 4; }   (32 or more bits consumed)
+  uint32_t lo = (uint32_t)b.cont, hi = (uint32_t)(b.cont >> 32);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.le.s32 p, %0, 20;\n\t"
+      "@p mov.b32 %2, %1;\n\t"
+      "@p mov.b32 %1, %3;\n\t"
+      "@p add.s32 %0, %0, 32;\n\t"
+      "@p ld.shared.u32 %3, [%4];\n\t"
+      "@p add.u32 %4, %4, -4;\n\t}"
+      : "+r"(b.s1), "+r"(lo), "+r"(hi), "+r"(b.next), "+r"(b.ra));
+  b.cont = ((uint64_t)hi << 32) | lo;
 }
-__device__ __forceinline__ uint32_t swin_decode(SmemWindow& b, const LutFull& lut, int32_t& rem) {
-  const uint32_t x = (uint32_t)(b.cont >> b.s);
-  const int32_t e = lut.get(x);
-  b.s += e >> 8;
-  rem += e >> 8;
-  return (uint32_t)e;
+// One symbol: the table entry (symbol in byte 0, minus the code length above it, sign-extended).
+__device__ __forceinline__ int32_t swin_entry(SmemWindow& b) {
+  const uint32_t x = (uint32_t)(b.cont >> b.s1);
+  const int32_t e = lds_s16((x & 0xFFEu) | b.lut_s);
+  b.s1 += e >> 8;
+  return e;
 }
 // Decode from bit offset `from` down to the first code boundary at or below `bound`.  -> symbols seen.
-__device__ __forceinline__ uint32_t swin_scan(SmemWindow& b, const LutFull& lut, uint32_t from, uint32_t bound, uint32_t& stop) {
+// Two symbols per test: a pair may run one symbol past the boundary (into readable bytes: the stream buffer
+// has kSyncPad bytes below the stream), which the exit undoes.
+__device__ __forceinline__ uint32_t swin_scan(SmemWindow& b, uint32_t from, uint32_t bound, uint32_t& stop) {
   int32_t rem = (int32_t)(from - bound);
   uint32_t n = 0;
   if (rem > 0) {
     swin_seek(b, from);
-    for (;;) {
+    int32_t rem1;
+    do {
       swin_refill(b);
-      swin_decode(b, lut, rem);
-      n++;
-      if (rem <= 0) break;
-      swin_decode(b, lut, rem);
-      n++;
-      if (rem <= 0) break;
+      rem1 = rem + (swin_entry(b) >> 8);
+      rem = rem1 + (swin_entry(b) >> 8);
+      n += 2;
+    } while (rem > 0);
+    if (rem1 <= 0) {  // the first symbol of the last pair already reached the boundary
+      rem = rem1;
+      n--;
     }
   }
   stop = (uint32_t)((int32_t)bound + rem);
   return n;
 }
-// Whole words where the thread owns all four bytes, single bytes at its two ends.
+// Symbols [off, off + n) of the quarter plane: single bytes up to the first word boundary, then four symbols
+// per 32-bit store, single bytes at the end (the neighbouring threads own the other bytes of those words).
+__device__ __forceinline__ void swin_emit(SmemWindow& b, uint32_t from, uint32_t n, uint8_t* plane, uint32_t off) {
+  if (n == 0) return;
+  swin_seek(b, from);
+  uint32_t pos = off;
+  const uint32_t end = off + n;
+  while (pos < end && (pos & 3u)) {
+    swin_refill(b);
+    plane[pos++] = (uint8_t)swin_entry(b);
+  }
+  for (; pos + 4 <= end; pos += 4) {
+    swin_refill(b);
+    const uint32_t e0 = (uint32_t)swin_entry(b), e1 = (uint32_t)swin_entry(b);
+    swin_refill(b);
+    const uint32_t e2 = (uint32_t)swin_entry(b), e3 = (uint32_t)swin_entry(b);
+    *reinterpret_cast<uint32_t*>(plane + pos) = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+  }
+  while (pos < end) {
+    swin_refill(b);
+    plane[pos++] = (uint8_t)swin_entry(b);
+  }
+}
+// Whole words where the thread owns all four bytes, single bytes at its two ends (ring fallback only).
 struct PlaneWriter {
   uint8_t* plane;
   uint32_t off, pos, acc;
@@ -143,23 +197,6 @@ struct PlaneWriter {
     }
   }
 };
-__device__ __forceinline__ void swin_emit(SmemWindow& b, const LutFull& lut, uint32_t from, uint32_t n, uint8_t* plane, uint32_t off) {
-  if (n == 0) return;
-  swin_seek(b, from);
-  int32_t dummy = 0;
-  PlaneWriter w(plane, off);
-  uint32_t i = 0;
-  for (; i + 2 <= n; i += 2) {
-    swin_refill(b);
-    w.put(swin_decode(b, lut, dummy) & 0xFFu);
-    w.put(swin_decode(b, lut, dummy) & 0xFFu);
-  }
-  if (i < n) {
-    swin_refill(b);
-    w.put(swin_decode(b, lut, dummy) & 0xFFu);
-  }
-  w.finish();
-}
 
 // ---- fallback: the stream stays in global memory, each thread feeds a private ring (decode.cuh) ----
 template <class LUT>
@@ -269,8 +306,12 @@ __global__ void __launch_bounds__(kParseWarps * 32) k_parse_tables(DecodeCfg cfg
 // items: hlist[0 .. ctrl->huf_count) = coded items (g * K + c) of chunks in fused or general mode.
 // One bitstream: work = 4 * (index into hlist) + stream.  The caller has synchronised the CTA since
 // the previous call (the shared state is reused).
+__device__ __forceinline__ bool off_in_slack(uint32_t lut_s, const SyncShared& S) {  // the table must end where S begins
+  return lut_s + 4096u != (uint32_t)__cvta_generic_to_shared(&S);
+}
 template <int G>
-__device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __restrict__ out, SyncShared& S, uint64_t work) {
+__device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __restrict__ out, SyncShared& S, uint16_t* lut_tab, uint32_t lut_s,
+                                             uint64_t work) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint64_t K = cfg.K;
   {
@@ -285,28 +326,28 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
     const ItemTable& T = cfg.tables[work >> 2];
     const int hsize = T.hsize, lg = T.lg, nsym = T.nsym;
     if (hsize < 0) return;  // (uniform; the parse kernel raised the error)
-    if (tid < kHufLogMax + 2) S.cls_count[tid] = 0;
-    S.weights[tid] = T.weights[tid];   // (kSyncThreads == 256)
+    if (tid < (kSyncThreads / 32) * 16) (&S.cls_warp[0][0])[tid] = 0;
     __syncthreads();
     // ---- full table, one thread per symbol (huf_decompress.c:151-183: weights ascending, symbols
-    //      ascending within a weight, 2^(w-1) consecutive entries each) ----
-    int w_mine = 0;
-    uint32_t rank = 0;
-    if (tid < nsym) {
-      w_mine = S.weights[tid];
-      if (w_mine) {
-        for (int m = 0; m < tid; m++) rank += (S.weights[m] == w_mine);
-        atomicAdd(&S.cls_count[w_mine], 1u);
-      }
-    }
+    //      ascending within a weight, 2^(w-1) consecutive entries each).  A symbol's rank inside its weight
+    //      class = equal weights among the lower lanes of its warp (one match + popc) + the class counts of
+    //      the warps below ----
+    const int w_mine = tid < nsym ? (int)T.weights[tid] : 0;
+    const uint32_t same = __match_any_sync(0xffffffffu, w_mine);
+    uint32_t rank = (uint32_t)__popc(same & ((1u << lane) - 1u));
+    if (w_mine && rank == 0) S.cls_warp[wid][w_mine] = (uint32_t)__popc(same);
     __syncthreads();
     if (tid == 0) {
       uint32_t at = 0;
       for (int w = 1; w <= lg; w++) {
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int q = 0; q < kSyncThreads / 32; q++) cnt += S.cls_warp[q][w];
         S.cls_start[w] = at;
-        at += (S.cls_count[w] << (w - 1)) << (kDecLutLog - lg);
+        at += (cnt << (w - 1)) << (kDecLutLog - lg);
       }
     }
+    for (int q = 0; q < wid; q++) rank += S.cls_warp[q][w_mine];
     __syncthreads();
     if (w_mine) {
       const int len = lg + 1 - w_mine;
@@ -315,10 +356,10 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
       const uint16_t e = (uint16_t)(tid | (((256 - len) & 0xFF) << 8));  // symbol | -length
       if (span >= 2) {
         const uint32_t ee = (uint32_t)e | ((uint32_t)e << 16);
-        uint32_t* p = reinterpret_cast<uint32_t*>(S.lut + u);  // u is a multiple of span, so even
+        uint32_t* p = reinterpret_cast<uint32_t*>(lut_tab + u);  // u is a multiple of span, so even
         for (uint32_t q = 0; q < (span >> 1); q++) p[q] = ee;
       } else {
-        S.lut[u] = e;
+        lut_tab[u] = e;
       }
     }
     // ---- this CTA's bitstream (jump table, huf_decompress.c:283-290) ----
@@ -351,7 +392,7 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
       if (tid == 0) atomicOr(&cfg.ctrl->error, kErrCorrupt);
       return;  // (uniform: every thread computed the same)
     }
-    const LutFull lut{S.lut, kDecLutLog};
+    const LutFull lut{lut_tab, kDecLutLog};   // (the ring fallback goes through the generic table type)
     const uint8_t* sp = p + s_off;                       // the bitstream: s_len bytes
     const bool in_smem = s_len <= kSyncStreamCap;        // (uniform)
     uint32_t mark, first;
@@ -370,6 +411,11 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
       cp_async_commit();
       cp_async_wait<0>();
       sw.base_s = (uint32_t)__cvta_generic_to_shared(S.sbuf);
+      sw.lut_s = lut_s;
+      if ((lut_s & 4095u) || off_in_slack(lut_s, S)) {  // cannot happen (sync_carve), but never decode wrongly
+        if (tid == 0) atomicOr(&cfg.ctrl->error, kErrUnsupported);
+        return;
+      }
       first = 8u * head;
       mark = 8u * (head + s_len - 1) + (uint32_t)hb32(lastb);
     } else {
@@ -387,7 +433,7 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
     uint32_t from = top, stop = top, n = 0;
     bool need = true;
     for (int round = 0; round <= kSyncThreads; round++) {
-      if (need) n = in_smem ? swin_scan(sw, lut, from, bound, stop) : sync_scan(b, lut, from, bound, stop);
+      if (need) n = in_smem ? swin_scan(sw, from, bound, stop) : sync_scan(b, lut, from, bound, stop);
       S.stop[tid] = stop;
       __syncthreads();
       const uint32_t nf = tid ? S.stop[tid - 1] : mark;
@@ -416,7 +462,7 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
       if (tid == 0) atomicOr(&cfg.ctrl->error, kErrCorrupt);
       return;  // (uniform)
     }
-    if (in_smem) swin_emit(sw, lut, from, n, S.plane, off);
+    if (in_smem) swin_emit(sw, from, n, S.plane, off);
     else sync_emit(b, lut, from, n, S.plane, off);
     __syncthreads();
     // ---- quarter plane -> elements, or -> the chunk's workspace plane ----
@@ -486,18 +532,20 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
 template <int G>
 __global__ void __launch_bounds__(kSyncThreads) k_huf_decode_sync(DecodeCfg cfg, uint8_t* __restrict__ out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  SyncShared& S = *reinterpret_cast<SyncShared*>(smem_raw);
+  const SyncCarve cv = sync_carve(smem_raw);
+  SyncShared& S = *cv.S;
   const uint32_t nh = cfg.ctrl->huf_count;
   for (uint64_t work = blockIdx.x; work < 4ull * nh; work += gridDim.x) {
     __syncthreads();  // the previous item's shared state is dead
-    sync_process<G>(cfg, out, S, work);
+    sync_process<G>(cfg, out, S, cv.lut, cv.lut_s, work);
   }
 }
 
 // Bitstreams of every tensor of a batch in one grid (flat index -> tensor by binary search).
 __global__ void __launch_bounds__(kSyncThreads) k_huf_decode_sync_batch(BatchCfg B) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  SyncShared& S = *reinterpret_cast<SyncShared*>(smem_raw);
+  const SyncCarve cv = sync_carve(smem_raw);
+  SyncShared& S = *cv.S;
   const uint64_t total = B.item_start[B.n];
   for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
     const uint32_t t = batch_find(B.item_start, B.n, w);
@@ -505,9 +553,9 @@ __global__ void __launch_bounds__(kSyncThreads) k_huf_decode_sync_batch(BatchCfg
     const uint64_t work = w - B.item_start[t];
     if (work >= 4ull * cfg.ctrl->huf_count) continue;  // (uniform) the bound counts every item, only the coded ones are queued
     __syncthreads();
-    if (cfg.G == 1) sync_process<1>(cfg, cfg.out, S, work);
-    else if (cfg.G == 2) sync_process<2>(cfg, cfg.out, S, work);
-    else sync_process<4>(cfg, cfg.out, S, work);
+    if (cfg.G == 1) sync_process<1>(cfg, cfg.out, S, cv.lut, cv.lut_s, work);
+    else if (cfg.G == 2) sync_process<2>(cfg, cfg.out, S, cv.lut, cv.lut_s, work);
+    else sync_process<4>(cfg, cfg.out, S, cv.lut, cv.lut_s, work);
   }
 }
 

@@ -378,12 +378,12 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
     int rc = dispatch_G(G, [&](auto g) -> int {
       constexpr int GG = decltype(g)::value;
       if (!attr_done[GG]) {
-        ZB_CUDA(cudaFuncSetAttribute(k_huf_decode_sync<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncShared)));
+        ZB_CUDA(cudaFuncSetAttribute(k_huf_decode_sync<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes));
         attr_done[GG] = true;
       }
       static const int nb = [] {
         int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_huf_decode_sync<GG>, kSyncThreads, sizeof(SyncShared)) != cudaSuccess || v < 1) v = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_huf_decode_sync<GG>, kSyncThreads, kSyncSmemBytes) != cudaSuccess || v < 1) v = 1;
         return v;
       }();
       const unsigned grid = (unsigned)std::min<uint64_t>(4 * nitems, (uint64_t)nb * sm_count_cached());
@@ -393,7 +393,7 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
         ZB_LAUNCHED();
       }
       ScopedTimer tm(kKHufDecodeSync, st);
-      k_huf_decode_sync<GG><<<grid, kSyncThreads, sizeof(SyncShared), st>>>(cfg, (uint8_t*)d_out);
+      k_huf_decode_sync<GG><<<grid, kSyncThreads, kSyncSmemBytes, st>>>(cfg, (uint8_t*)d_out);
       ZB_LAUNCHED();
       return ZIPNN_B200_OK;
     });
@@ -586,12 +586,12 @@ int zipnn_b200_decompress_batch(const zipnn_b200_batch_item* items, int n, void*
     {
       static bool attr_done = false;
       if (!attr_done) {
-        ZB_CUDA(cudaFuncSetAttribute(k_huf_decode_sync_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncShared)));
+        ZB_CUDA(cudaFuncSetAttribute(k_huf_decode_sync_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyncSmemBytes));
         attr_done = true;
       }
       static const int nb = [] {
         int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_huf_decode_sync_batch, kSyncThreads, sizeof(SyncShared)) != cudaSuccess || v < 1) v = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_huf_decode_sync_batch, kSyncThreads, kSyncSmemBytes) != cudaSuccess || v < 1) v = 1;
         return v;
       }();
       const unsigned grid = (unsigned)std::min<uint64_t>(item_start[n], (uint64_t)nb * sms);
@@ -601,7 +601,7 @@ int zipnn_b200_decompress_batch(const zipnn_b200_batch_item* items, int n, void*
         ZB_LAUNCHED();
       }
       ScopedTimer tm(kKHufDecodeSync, st);
-      k_huf_decode_sync_batch<<<grid, kSyncThreads, sizeof(SyncShared), st>>>(B);
+      k_huf_decode_sync_batch<<<grid, kSyncThreads, kSyncSmemBytes, st>>>(B);
       ZB_LAUNCHED();
     }
     {
