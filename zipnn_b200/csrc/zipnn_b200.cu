@@ -178,8 +178,8 @@ inline uint64_t num_chunks(size_t n, size_t chunk) { return (n + chunk - 1) / ch
 // general chunks, e.g. fp32 tensors upcast from bf16).
 constexpr uint64_t kDefaultSlots = 64;
 constexpr uint64_t kSyncTablesMaxChunks = 16384;  // largest tensor the sync decoder can be asked to take (ZIPNN_B200_SYNC_MAX is clamped to it)
-constexpr uint64_t kSyncDefaultMaxChunks = 3072;  // measured crossover with the one-thread-per-bitstream kernels: 256 MiB 0.52 vs 1.5 ms,
-                                                  // 1 GiB 2.0 vs 1.55 ms (profiles/r2_kernel_times.jsonl)
+constexpr uint64_t kSyncDefaultMaxChunks = 4096;  // measured crossover with the one-thread-per-bitstream kernels (bf16): 256 MiB 0.39 vs
+                                                  // 1.5 ms, 1 GiB 1.45 vs 1.50 ms, 4 GiB ~5.7 vs 2.1 (profiles/r2_kernel_times.jsonl)
 struct DecWs {
   size_t items_off, mode_off, slot_off, rlist_off, olist_off, hlist_off, tables_off, fill_off, planes_off, pstride, fixed;
 };
