@@ -939,15 +939,10 @@ __device__ __forceinline__ void take16(const uint4& a, const uint4& b, uint32_t 
   for (int i = 0; i < 4; i++) out[i] = s4 ? u[i + 1] : u[i];
 }
 
-// Un-rotate at plane level: the two top byte planes hold [sign|mant7] (lo) and [exponent] (hi)
-// of every element; the element's real top bytes are hi' = sign|exp>>1, lo' = exp<<7|mant7.
-// 4 ops per 4 elements instead of 5 per 32-bit word after interleaving.
-__device__ __forceinline__ void unrotate_planes(uint32_t& lo, uint32_t& hi) {
-  const uint32_t sm = lo, e = hi;
-  hi = (sm & 0x80808080u) | ((e >> 1) & 0x7F7F7F7Fu);
-  lo = ((e << 7) & 0x80808080u) | (sm & 0x7F7F7F7Fu);
-}
-// The same with the exponent bytes already rotated right by one (lut_symbol): two bit selects, written as
+// Un-rotate at plane level: the two top byte planes hold [sign|mant7] (lo) and [exponent] (hi) of every element;
+// the element's real top bytes are hi' = sign | exp >> 1, lo' = exp << 7 | mant7.
+// The fused kernel's tables hold the exponent bytes already rotated right by one (lut_symbol), E = ror8(exp), so
+// hi' = (E & 0x7F) | (sm & 0x80), lo' = (E & 0x80) | (sm & 0x7F): two bit selects per four elements, written as
 // LOP3 because the compiler splits each into two operations.
 __device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m) {  // (a & m) | (b & ~m)
   uint32_t d;

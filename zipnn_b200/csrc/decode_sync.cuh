@@ -53,6 +53,7 @@ struct SyncShared {
   __align__(16) uint8_t plane[kHufBlockMax / 4 + 16];  // the decoded quarter plane
 };
 static_assert(sizeof(((SyncShared*)0)->sbuf) >= kSyncThreads * kRingBytes, "the fallback rings alias the stream buffer");
+static_assert(sizeof(((SyncShared*)0)->plane) >= 2u * 32u * kSyncThreads, "the checkpoints of the scan passes alias the plane");
 // Parsed table description of one coded item (k_parse_tables -> k_huf_decode_sync), in the workspace.
 struct ItemTable {
   uint8_t weights[256];
@@ -129,10 +130,14 @@ __device__ __forceinline__ int32_t swin_entry(SmemWindow& b) {
 }
 // Decode from bit offset `from` down to the first code boundary at or below `bound`.  -> symbols seen.
 // Two symbols per test: a pair may run one symbol past the boundary (into readable bytes: the stream buffer
-// has kSyncPad bytes below the stream), which the exit undoes.
-__device__ __forceinline__ uint32_t swin_scan(SmemWindow& b, uint32_t from, uint32_t bound, uint32_t& stop) {
+// has kSyncPad bytes below the stream), which the exit undoes.  Every eighth code boundary is RECORDED (its
+// distance to `bound`, checkpoint j after 8 (j + 1) symbols, cp[j * kSyncThreads + tid]): a later pass that starts
+// somewhere else only has to decode until it stands on one of them (swin_rescan).
+constexpr int kSyncCheckpoints = 32;   // per thread; segments with more than 256 symbols record only their first 256
+__device__ __forceinline__ uint32_t swin_scan(SmemWindow& b, uint32_t from, uint32_t bound, uint32_t& stop, uint16_t* cp, int tid, int& ncp) {
   int32_t rem = (int32_t)(from - bound);
   uint32_t n = 0;
+  ncp = 0;
   if (rem > 0) {
     swin_seek(b, from);
     int32_t rem1;
@@ -141,12 +146,45 @@ __device__ __forceinline__ uint32_t swin_scan(SmemWindow& b, uint32_t from, uint
       rem1 = rem + (swin_entry(b) >> 8);
       rem = rem1 + (swin_entry(b) >> 8);
       n += 2;
+      if ((n & 7u) == 0 && rem > 0 && n <= 8u * kSyncCheckpoints) cp[((n >> 3) - 1u) * kSyncThreads + (uint32_t)tid] = (uint16_t)rem;
     } while (rem > 0);
     if (rem1 <= 0) {  // the first symbol of the last pair already reached the boundary
       rem = rem1;
       n--;
     }
+    const uint32_t full = (rem > 0 ? n : n - 1u) >> 3;   // (n - 1: a checkpoint is only written while rem > 0)
+    ncp = (int)(full < (uint32_t)kSyncCheckpoints ? full : (uint32_t)kSyncCheckpoints);
   }
+  stop = (uint32_t)((int32_t)bound + rem);
+  return n;
+}
+// The same segment again from another start (`from` <= the start of the recorded pass): decoding is deterministic,
+// so from the first recorded boundary it stands on, this pass would repeat the recorded one -- its stop is the
+// recorded stop and its symbol count = symbols up to that boundary + what the recorded pass (n_rec symbols) had
+// left after it.  Huffman codes synchronise within a few symbols, so this costs ~15 symbols instead of a segment.
+// Returns the symbol count; if the boundary is reached without a match the checkpoints are dropped and
+// `stop` is this pass's own.
+__device__ __forceinline__ uint32_t swin_rescan(SmemWindow& b, uint32_t from, uint32_t bound, uint32_t& stop, const uint16_t* cp, int tid, int& ncp,
+                                                uint32_t n_rec) {
+  int32_t rem = (int32_t)(from - bound);
+  uint32_t n = 0;
+  if (rem > 0) {
+    swin_seek(b, from);
+    int j = 0;
+    int32_t c = ncp ? (int32_t)cp[tid] : -1;
+    for (;;) {
+      swin_refill(b);
+      rem += swin_entry(b) >> 8;
+      n++;
+      if (rem <= 0) break;
+      while (c > rem) {
+        j++;
+        c = j < ncp ? (int32_t)cp[(uint32_t)j * kSyncThreads + (uint32_t)tid] : -1;
+      }
+      if (c == rem) return n + n_rec - 8u * (uint32_t)(j + 1);
+    }
+  }
+  ncp = 0;
   stop = (uint32_t)((int32_t)bound + rem);
   return n;
 }
@@ -430,10 +468,20 @@ __device__ __forceinline__ void sync_process(const DecodeCfg& cfg, uint8_t* __re
     if (segbits < kSyncMinSegBits) segbits = kSyncMinSegBits;
     const uint32_t top = (uint64_t)tid * segbits < bits ? mark - (uint32_t)tid * segbits : first;          // guess (exact for tid 0)
     const uint32_t bound = (uint64_t)(tid + 1) * segbits < bits ? mark - (uint32_t)(tid + 1) * segbits : first;
-    uint32_t from = top, stop = top, n = 0;
+    uint32_t from = top, stop = top, n = 0, n_rec = 0;
+    int ncp = 0;                                                    // recorded boundaries of this thread's first pass
+    uint16_t* cp = reinterpret_cast<uint16_t*>(S.plane);            // [kSyncCheckpoints][kSyncThreads]; the plane is written after the rounds
     bool need = true;
     for (int round = 0; round <= kSyncThreads; round++) {
-      if (need) n = in_smem ? swin_scan(sw, from, bound, stop) : sync_scan(b, lut, from, bound, stop);
+      if (need) {
+        if (!in_smem) {
+          n = sync_scan(b, lut, from, bound, stop);
+        } else if (ncp == 0) {
+          n = n_rec = swin_scan(sw, from, bound, stop, cp, tid, ncp);
+        } else {
+          n = swin_rescan(sw, from, bound, stop, cp, tid, ncp, n_rec);
+        }
+      }
       S.stop[tid] = stop;
       __syncthreads();
       const uint32_t nf = tid ? S.stop[tid - 1] : mark;
