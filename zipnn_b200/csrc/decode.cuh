@@ -445,22 +445,25 @@ struct LutCol {
   static_assert(PB == 5, "the one-instruction address needs 2^(11-PB) = 64 bytes = one row of 32 u16");
   uint32_t col_s;   // shared-space address of this lane's entry 0 (2 KiB aligned array + 2 * lane)
   uint32_t tail_s;
-  uint32_t x_long;
+  uint32_t hi_mask; // index bits that are all zero exactly for the indices the tail serves: 0x7FF & ~(x_cut - 1)
   __device__ __forceinline__ int32_t get(uint32_t x) const {
-    // ONE load per symbol: the address is SELECTED between the lane's column and the chunk's tail
-    // (idx < x_long ? tail_s + 2 * idx : (x & 0x7C0) | col_s).  Written as PTX because the compiler turns the C++
-    // form into five instructions (idx, x + x, & 0xFFE, compare, predicated add) where three do (idx, compare,
-    // predicated multiply-add); removing the tail lookup altogether -- wrong, timing only -- gave 8.76 -> 7.44 ms,
-    // so each instruction here is ~1.5 % of the kernel.
+    // ONE load per symbol: the address is SELECTED between the lane's column and the chunk's tail,
+    //   (idx & hi_mask) == 0 ? tail_s + 2 * idx : (x & 0x7C0) | col_s.
+    // The tail serves every index below x_cut = the power of two at or above the canonical bound x_long of the
+    // codes longer than 5 bits (fill_lut_col copies the few short codes below x_cut into it as well), so that the
+    // test is ONE operation on the peeked word (`LOP3` with a predicate result) instead of mask + compare: the
+    // test sits on the symbol-to-symbol dependent chain (peek -> test -> select -> load -> advance), which is what
+    // the kernel's time follows.  Written as PTX because the compiler turns the C++ form into five instructions.
     int32_t v;
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 i, a;\n\t"
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 i, a, t;\n\t"
+        "and.b32 t, %1, %4;\n\t"
+        "setp.eq.u32 p, t, 0;\n\t"
         "and.b32 i, %1, 0x7FF;\n\t"
         "lop3.b32 a, %1, 0x7C0, %2, 0xEA;\n\t"
-        "setp.lt.u32 p, i, %4;\n\t"
         "@p mad.lo.u32 a, i, 2, %3;\n\t"
         "ld.shared.s16 %0, [a];\n\t}"
         : "=r"(v)
-        : "r"(x), "r"(col_s), "r"(tail_s), "r"(x_long));
+        : "r"(x), "r"(col_s), "r"(tail_s), "r"(hi_mask));
     return v;
   }
 };
@@ -471,7 +474,8 @@ struct LutCol {
 // bit selects per four elements, hi' = (E & 0x7F) | (sm & 0x80), lo' = (E & 0x80) | (sm & 0x7F).
 __device__ __forceinline__ uint32_t lut_symbol(uint32_t n, bool pre_rot) { return pre_rot ? ((n >> 1) | ((n & 1u) << 7)) : n; }
 
-// Tail size for a PB-bit primary: index bound of the codes longer than PB bits (or -1).
+// Tail size for a PB-bit primary (or -1): x_cut, the power of two (>= 64) at or above the index bound x_long of the
+// codes longer than PB bits.  Typical exponent planes: x_long = 64 or 128.
 __device__ __forceinline__ int lut_tail_size(const uint8_t* weights, int nsym, int lg, int pb) {
   if (lg > kDecLutLog) return -1;
   uint32_t cnt[kHufLogMax + 2];
@@ -483,13 +487,15 @@ __device__ __forceinline__ int lut_tail_size(const uint8_t* weights, int nsym, i
     at += (cnt[w] << (w - 1)) << (kDecLutLog - lg);
     if (lg + 1 - w > pb) x_long = at;
   }
-  return (int)x_long;
+  uint32_t x_cut = 64;
+  while (x_cut < x_long) x_cut <<= 1;
+  return (int)x_cut;
 }
 
 // Fill one lane's column (all 4 lanes of a chunk run it) and, when `with_tail`, the chunk's tail.
 template <int PB>
 __device__ __forceinline__ void fill_lut_col(uint16_t* col /* entry k at col[32 * k] */, uint16_t* tail, bool with_tail,
-                                             const uint8_t* weights, int nsym, int lg, bool pre_rot) {
+                                             const uint8_t* weights, int nsym, int lg, bool pre_rot, uint32_t x_cut) {
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
   for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
@@ -516,6 +522,10 @@ __device__ __forceinline__ void fill_lut_col(uint16_t* col /* entry k at col[32 
     } else {
       const uint32_t p0 = u >> (kDecLutLog - PB), pn = span >> (kDecLutLog - PB);
       for (uint32_t q = 0; q < pn; q++) col[32 * (p0 + q)] = (uint16_t)e;
+      if (with_tail && u < x_cut) {  // the tail serves every index below x_cut (LutCol::get)
+        const uint32_t end = u + span < x_cut ? u + span : x_cut;
+        for (uint32_t q = u; q < end; q++) tail[q] = (uint16_t)e;
+      }
     }
   }
 }
@@ -533,6 +543,21 @@ __device__ __forceinline__ uint32_t window_decode(BitWindow& b, const LUT& lut) 
   return (uint32_t)e;  // symbol in byte 0
 }
 
+// Two symbols around one refill.  The first peek is taken BEFORE the refill: s >= 0 there (<= 31 bits are consumed
+// after a refill and <= 22 by the pair since), and a refill only re-bases `cont` and `s` -- the peeked bits are the
+// same -- so the compare / select / add of the refill leave the symbol-to-symbol dependent chain (advance -> peek ->
+// index -> compare -> select -> load -> advance), which is what the kernel's time follows, and run in
+// the shadow of the first table load instead.
+template <class LUT>
+__device__ __forceinline__ void window_pair(BitWindow& b, const LUT& lut, uint32_t& e0, uint32_t& e1) {
+  const uint32_t x0 = (uint32_t)(b.cont >> b.s);
+  window_refill(b);
+  const int32_t a = lut.get(x0);
+  b.s += a >> 8;
+  e0 = (uint32_t)a;
+  e1 = window_decode(b, lut);
+}
+
 // 16 symbols -> 4 words (symbol j in byte j).  Ring maintenance for the NEXT iterations is
 // issued first so the copies overlap the decode.
 template <class LUT>
@@ -545,10 +570,9 @@ __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t 
     cp_async_commit();
 #pragma unroll
     for (int q = 2 * h; q < 2 * h + 2; q++) {
-      window_refill(b);
-      const uint32_t e0 = window_decode(b, lut), e1 = window_decode(b, lut);
-      window_refill(b);
-      const uint32_t e2 = window_decode(b, lut), e3 = window_decode(b, lut);
+      uint32_t e0, e1, e2, e3;
+      window_pair(b, lut, e0, e1);
+      window_pair(b, lut, e2, e3);
       o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
     }
     cp_async_wait<1>();  // everything but the group just committed has landed
@@ -819,21 +843,24 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Shared memory of one warp (dynamic; offsets from the 1 KiB aligned base, A = its shared address):
+// Shared memory of one warp (dynamic; offsets from the 1 KiB aligned base, A = its shared address).  The number of
+// resident warps is what the kernel's speed follows (8 warps/SM 12.0 ms ... 15 warps 8.4 ms), and
+// shared memory is what limits it, so nothing here is slack:
 //   PB = 5 (bf16 / fp32 exponent planes):
 //     cols  [32][32] u16   2 KiB   private 5-bit columns; must start on a 2 KiB boundary of the shared
 //                                  address space (LutCol): at A's next 2 KiB boundary, 0 or 1 KiB in
-//     gap                  1 KiB   the other KiB of the first three: side tiles / slots go here
+//     ring lanes 0..15     1 KiB   the other KiB of the first three
 //   PB = 0 (fp16 / fp8): prim [8][256] u16, 4 KiB
-//   tail  [tail_cap] u16           tail tables of the 8 chunks packed back to back; the last 16 bytes
-//                                  of its 2 (4) KiB hold the two mbarriers
-//   ring  [32][64]         2 KiB   per-lane stream ring; weights[8][256] alias it during the parse
+//   tail  [tail_cap] u16   2 (4) KiB  tail tables of the 8 chunks packed back to back (8 x 128 entries fit exactly)
+//   ring  [..][64]                 per-lane stream rings (PB = 5: lanes 16..31, 1 KiB; PB = 0: all 32, 2 KiB);
+//                                  weights[8][256] alias the two halves during the parse
 //   stage [32][128]        4 KiB   one 128-byte output row per lane (1 KiB aligned, 16-byte units XOR-
 //                                  swizzled by the row); the tANS scratch of the parse aliases it
 //   side                           cp.async path: (G-1) x 2 KiB of slots (4 x 16 bytes per lane and plane);
 //                                  bulk-tensor path (16-bit types): 2 stages x [32 lanes][48 bytes] = 3 KiB.
 //                                  The two uses alias.
-// bf16: 2 + 1 + 2 + 2 + 4 + 3 = 14 KiB -> 15 warps per SM;  fp32: 3 + 2 + 2 + 4 + 6 = 17 KiB -> 12.
+//   bars                   16 B    the two mbarriers
+// bf16: 2 + 1 + 2 + 1 + 4 + 3 = 13 KiB -> 16 warps per SM;  fp32: 3 + 2 + 1 + 4 + 6 = 16 KiB -> 13.
 template <int G>
 struct FusedGeom {
   static constexpr int kIters = 8 / G;                 // iterations (16 symbols) per 128-byte output row
@@ -848,19 +875,21 @@ struct FusedGeom {
   static constexpr uint32_t kSideAll = kSlotRegion > kTileRegion ? kSlotRegion : kTileRegion;
 };
 __host__ __device__ constexpr uint32_t fused_tail_bytes(int pb) { return pb == 0 ? 4096u : 2048u; }
-__host__ __device__ constexpr uint32_t fused_tail_cap(int pb) { return (fused_tail_bytes(pb) - 16u) / 2u; }  // entries (multiple of 8)
+__host__ __device__ constexpr uint32_t fused_tail_cap(int pb) { return fused_tail_bytes(pb) / 2u; }  // entries: 8 chunks x 128 fit exactly
 template <int G>
 __host__ __device__ constexpr size_t fused_smem_bytes(int pb) {
-  return (pb == 0 ? (size_t)4096 : (size_t)3072) + FusedGeom<G>::kSideAll + fused_tail_bytes(pb) + 32 * kRingBytes + 32 * 128;
+  return (pb == 0 ? (size_t)4096 + 32 * kRingBytes : (size_t)3072 + 16 * kRingBytes) + FusedGeom<G>::kSideAll + fused_tail_bytes(pb) + 32 * 128 + 16;
 }
 struct FusedSmem {
   unsigned char* raw;
   uint32_t base_s;     // shared address of raw
   uint32_t table_off;  // cols (PB = 5) or prim (PB = 0)
-  uint32_t gap_off;    // PB = 5: the free KiB next to the columns
-  uint32_t tail_off, bar_off, ring_off, stage_off, side_off;
+  uint32_t ring_lo_off, ring_hi_off;  // rings of lanes 0..15 / 16..31 (PB = 5: the first half fills the KiB next to the columns)
+  uint32_t tail_off, bar_off, stage_off, side_off;
   __device__ __forceinline__ uint16_t* tail() const { return reinterpret_cast<uint16_t*>(raw + tail_off); }
-  __device__ __forceinline__ uint8_t (*ring() const)[kRingBytes] { return reinterpret_cast<uint8_t (*)[kRingBytes]>(raw + ring_off); }
+  __device__ __forceinline__ uint8_t* ring(int lane) const { return raw + (lane < 16 ? ring_lo_off : ring_hi_off) + kRingBytes * (uint32_t)(lane & 15); }
+  // parse scratch: 256 weight bytes per chunk slot, four slots in each half of the rings
+  __device__ __forceinline__ uint8_t* weights(int slot) const { return raw + (slot < 4 ? ring_lo_off : ring_hi_off) + 256u * (uint32_t)(slot & 3); }
   __device__ __forceinline__ uint8_t (*stage() const)[128] { return reinterpret_cast<uint8_t (*)[128]>(raw + stage_off); }
 };
 template <int G, int PB>
@@ -875,21 +904,24 @@ __device__ __forceinline__ FusedSmem fused_smem_carve(unsigned char* raw) {
   uint32_t at;
   if (PB == 0) {
     S.table_off = 0;
-    S.gap_off = 0;
     at = 4096;
   } else {
     S.table_off = (2048u - (S.base_s & 2047u)) & 2047u;  // 0 or 1024 for a 1 KiB aligned base
-    S.gap_off = S.table_off ? 0u : 2048u;
+    S.ring_lo_off = S.table_off ? 0u : 2048u;
     at = 3072;
   }
   S.tail_off = at;
-  S.bar_off = at + fused_tail_bytes(PB) - 16u;
   at += fused_tail_bytes(PB);
-  S.ring_off = at;
-  at += 32 * kRingBytes;
+  if (PB == 0) {
+    S.ring_lo_off = at;
+    at += 16 * kRingBytes;
+  }
+  S.ring_hi_off = at;
+  at += 16 * kRingBytes;
   S.stage_off = at;  // 1 KiB multiple in both layouts
   at += 32 * 128;
   S.side_off = at;
+  S.bar_off = at + FusedGeom<G>::kSideAll;  // the two mbarriers, 16 bytes behind everything else
   return S;
 }
 // Shared address of side-tile stage st / of plane g's cp.async slots (both inside the side region).
@@ -1086,7 +1118,7 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
     int lg = 0, hsize = -1, x_long = 0;
     uint32_t tail_at = 0;
     {
-      uint8_t* weights = &S.ring()[0][0] + slot * 256;
+      uint8_t* weights = S.weights(slot);
       const bool builder = active && stream == 0;
       int nsym = 0;
       if (builder) {
@@ -1126,7 +1158,7 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
       if (PB != 0) {  // private columns: the 4 lanes of a chunk fill their own copy in parallel
         nsym = __shfl_sync(0xffffffffu, nsym, lane & ~3);
         if (active && hsize >= 0)
-          fill_lut_col<(PB ? PB : 5)>(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + lane, S.tail() + tail_at, stream == 0, weights, nsym, lg, rot);
+          fill_lut_col<(PB ? PB : 5)>(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + lane, S.tail() + tail_at, stream == 0, weights, nsym, lg, rot, (uint32_t)x_long);
       }
       __syncwarp();  // the ring and the stage (aliased by the parse scratch) are free from here on
     }
@@ -1166,7 +1198,11 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
       lut.col_s = S.base_s + S.table_off + 2u * (uint32_t)lane;
     }
     lut.tail_s = S.base_s + S.tail_off + 2u * tail_at;
-    lut.x_long = (uint32_t)x_long;
+    if constexpr (PB == 0) {
+      lut.x_long = (uint32_t)x_long;
+    } else {
+      lut.hi_mask = 0x7FFu & ~((uint32_t)x_long - 1u);   // x_long holds x_cut here (lut_tail_size)
+    }
 
     // ---- which way do the other planes and the output travel?  (warp-uniform) ----
     // Bulk tensor copies need all 32 lanes live on full chunks and every other plane stored raw at its
@@ -1184,7 +1220,7 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
     const bool side_tma = (G == 2) && regular && (cfg.tma_flags & kTmaSide);
 
     BitWindow b;
-    if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring()[lane])) {
+    if (live && !window_init(b, p + s_off, s_len, cfg.body, S.ring(lane))) {
       atomicOr(&cfg.ctrl->error, kErrCorrupt);
       live = false;
     }
@@ -1192,7 +1228,7 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
     //  lane decoding garbage from its zeroed window -- the error bit is already set, the output is discarded)
     if (regular && !live) {
       b.cont = 0; b.s = 53; b.qm = 0; b.next = 0; b.fetch = 0; b.floor_off = 0xffffffffu; b.start_bit = 0;
-      b.ring = S.ring()[lane];
+      b.ring = S.ring(lane);
       b.ring_s = (uint32_t)__cvta_generic_to_shared(b.ring);
       b.gbase = cfg.body;
     }
@@ -1208,12 +1244,14 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
         // memory without a single LSU instruction (the cp.async path pays 32 L1 wavefronts per instruction because
         // every lane's 16 bytes lie in a different line: a fifth of the kernel's LSU time).
         const uint32_t y0 = (uint32_t)(grp * 32u);
-        const uint32_t ntiles = rows_full * 2u;
+        constexpr int kTI = Geo::kTileIters;              // iterations served by one tile
+        constexpr int kTilesPerRow = kIters / kTI;
+        const uint32_t ntiles = rows_full * (uint32_t)kTilesPerRow;
         const uint32_t r0 = cfg.side_r0[0];
         auto issue_tile = [&](uint32_t t) {
           const uint32_t st = (tiles_done + t) & 1u;
           mbar_expect_tx(bar_s + 8u * st, Geo::kTileBytes);
-          tma_load_2d(side_tile_s<G>(S, st), &maps.side[0], 32u * t, y0, bar_s + 8u * st);
+          tma_load_2d(side_tile_s<G>(S, st), &maps.side[0], 16u * (uint32_t)kTI * t, y0, bar_s + 8u * st);
         };
         if (lane == 0 && ntiles) issue_tile(0);
         // the 8 stage rows this lane writes out each round: row r*4 + lane/8, 16-byte unit lane%8
@@ -1223,20 +1261,22 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
         for (int r = 0; r < 8; r++) row_out[r] = __shfl_sync(0xffffffffu, my_out, r * 4 + (lane >> 3)) + (uint64_t)(lane & 7) * 16;
         for (uint32_t row = 0; row < rows_full; row++) {
 #pragma unroll
-          for (int tr = 0; tr < 2; tr++) {
-            const uint32_t t = row * 2u + (uint32_t)tr;
+          for (int tr = 0; tr < kTilesPerRow; tr++) {
+            const uint32_t t = row * (uint32_t)kTilesPerRow + (uint32_t)tr;
             const uint32_t n = tiles_done + t;
             __syncwarp();  // every lane has read tile t-1: its stage may be overwritten by tile t+1
             if (lane == 0 && t + 1 < ntiles) issue_tile(t + 1);
             mbar_wait(bar_s + 8u * (n & 1u), (n >> 1) & 1u);
             const uint32_t my_row = side_tile_s<G>(S, n & 1u) + (uint32_t)lane * Geo::kTileRow;
-            const uint4 b0 = lds_u128(my_row), b1 = lds_u128(my_row + 16u), b2 = lds_u128(my_row + 32u);
+            uint4 blk[kTI + 1];
 #pragma unroll
-            for (int ki = 0; ki < 2; ki++) {
+            for (int q = 0; q <= kTI; q++) blk[q] = lds_u128(my_row + 16u * (uint32_t)q);
+#pragma unroll
+            for (int ki = 0; ki < kTI; ki++) {
               uint32_t pl[G][4];
               decode16(b, lut, pl[G - 1]);
-              take16(ki ? b1 : b0, ki ? b2 : b1, r0, pl[0]);
-              emit_elements<G>(pl, rot, stage, lane, (tr * 2 + ki) * G);
+              take16(blk[ki], blk[ki + 1], r0, pl[0]);
+              emit_elements<G>(pl, rot, stage, lane, (tr * kTI + ki) * G);
             }
           }
           __syncwarp();

@@ -128,6 +128,13 @@ __device__ __forceinline__ int32_t swin_entry(SmemWindow& b) {
   b.s1 += e >> 8;
   return e;
 }
+// Two symbols after one refill.  (The fused kernel peeks the first one BEFORE the refill, window_pair in decode.cuh;
+// here the shift is one lower, s1 = -1 is possible in front of a refill, and the peek has to follow it.)
+__device__ __forceinline__ void swin_pair(SmemWindow& b, int32_t& e0, int32_t& e1) {
+  swin_refill(b);
+  e0 = swin_entry(b);
+  e1 = swin_entry(b);
+}
 // Decode from bit offset `from` down to the first code boundary at or below `bound`.  -> symbols seen.
 // Two symbols per test: a pair may run one symbol past the boundary (into readable bytes: the stream buffer
 // has kSyncPad bytes below the stream), which the exit undoes.  Every eighth code boundary is RECORDED (its
@@ -142,9 +149,10 @@ __device__ __forceinline__ uint32_t swin_scan(SmemWindow& b, uint32_t from, uint
     swin_seek(b, from);
     int32_t rem1;
     do {
-      swin_refill(b);
-      rem1 = rem + (swin_entry(b) >> 8);
-      rem = rem1 + (swin_entry(b) >> 8);
+      int32_t e0, e1;
+      swin_pair(b, e0, e1);
+      rem1 = rem + (e0 >> 8);
+      rem = rem1 + (e1 >> 8);
       n += 2;
       if ((n & 7u) == 0 && rem > 0 && n <= 8u * kSyncCheckpoints) cp[((n >> 3) - 1u) * kSyncThreads + (uint32_t)tid] = (uint16_t)rem;
     } while (rem > 0);
@@ -200,10 +208,9 @@ __device__ __forceinline__ void swin_emit(SmemWindow& b, uint32_t from, uint32_t
     plane[pos++] = (uint8_t)swin_entry(b);
   }
   for (; pos + 4 <= end; pos += 4) {
-    swin_refill(b);
-    const uint32_t e0 = (uint32_t)swin_entry(b), e1 = (uint32_t)swin_entry(b);
-    swin_refill(b);
-    const uint32_t e2 = (uint32_t)swin_entry(b), e3 = (uint32_t)swin_entry(b);
+    int32_t e0, e1, e2, e3;
+    swin_pair(b, e0, e1);
+    swin_pair(b, e2, e3);
     *reinterpret_cast<uint32_t*>(plane + pos) = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
   }
   while (pos < end) {
