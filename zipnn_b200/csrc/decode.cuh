@@ -315,9 +315,9 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
 #pragma unroll 2
   for (int i = 0; i < maxn; i++) {
     const uint32_t f = b.fetch - 16;
-    // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above q = qm + 8
-    // (the container and `next` are in registers; later reads are at q - 8 and below)
-    if (b.fetch >= 16 + b.floor_off && f + (kRingBytes - 8) >= b.qm) {
+    // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above qm + 4 (the container and
+    // `next` hold everything from there up; later reads are at qm and below)
+    if (b.fetch >= 16 + b.floor_off && f + (kRingBytes - 4) >= b.qm) {
       cp_async16_s(b.ring_s | (f & (kRingBytes - 16)), b.gbase + f);  // f is a multiple of 16; the ring is ring-size aligned
       b.fetch = f;
     }
@@ -562,8 +562,14 @@ __device__ __forceinline__ void window_pair(BitWindow& b, const LUT& lut, uint32
 // issued first so the copies overlap the decode.
 template <class LUT>
 __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t (&o)[4]) {
-  // The ring is 64 bytes: one block is requested per 8 symbols (<= 11 bytes consumed), and a block
-  // is first read at least one half-iteration after the wait that covers it (see ring_top_up).
+  // The ring is 64 bytes and one block is requested per 8 symbols (one "half").  With span = requested bytes not
+  // yet read (qm + 4 - fetch, a multiple of 4) a block is requested when span <= 48; a half moves qm by <= 12 bytes
+  // (88 bits + a leftover of < 32 = three refills), so after every request span >= 56 (no request: >= 52), and the
+  // block just requested, the lowest 16 bytes of the span, is first read when span < 20: more than 36 bytes = more
+  // than THREE halves later.  It therefore only has to have landed at the end of the half after next:
+  // cp.async.wait_group 2 -- a lead of ~3000 cycles, which covers a block that comes from DRAM (with wait_group 1
+  // 7 % of the kernel's samples sat behind this wait).  Side-plane slots (cp.async path) ride the same groups: the
+  // block requested at the top of iteration k is read at the end of iteration k + 1, four halves later.
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     ring_top_up(b, 1);
@@ -575,7 +581,7 @@ __device__ __forceinline__ void decode16(BitWindow& b, const LUT& lut, uint32_t 
       window_pair(b, lut, e2, e3);
       o[q] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
     }
-    cp_async_wait<1>();  // everything but the group just committed has landed
+    cp_async_wait<2>();  // everything but the two newest groups has landed
   }
 }
 

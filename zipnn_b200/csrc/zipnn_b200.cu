@@ -338,9 +338,12 @@ static int fill_decode_cfg(DecodeCfg& cfg, const void* d_body, size_t body_len, 
   cfg.tables = (ItemTable*)(ws + L.tables_off);
   return ZIPNN_B200_OK;
 }
-static uint64_t sync_max_chunks() {
+static uint64_t sync_max_chunks(int G) {
   const Knobs kn = knobs();
-  return std::min<uint64_t>(kn.sync_max >= 0 ? (uint64_t)kn.sync_max : kSyncDefaultMaxChunks, kSyncTablesMaxChunks);
+  // four-plane types: the CTA's merge phase writes twice as much per decoded symbol, the crossover is lower
+  // (fp32 1 GiB: 1.68 ms against 1.29 for the one-thread kernel, profiles/r2_sweep_1gpu.jsonl)
+  const uint64_t dflt = G == 4 ? (kSyncDefaultMaxChunks * 3) / 4 : kSyncDefaultMaxChunks;
+  return std::min<uint64_t>(kn.sync_max >= 0 ? (uint64_t)kn.sync_max : dflt, kSyncTablesMaxChunks);
 }
 
 int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int bits_mode, int bytes_mode,
@@ -356,7 +359,7 @@ int zipnn_b200_decompress(const void* d_body, size_t body_len, int num_buf, int 
   // Small and medium tensors: one CTA per bitstream (decode_sync.cuh) instead of one thread per bitstream.
   // The one-thread kernels take ~2.2 ms for anything up to ~20 000 chunks (a bitstream is serial); the
   // per-bitstream CTAs cost ~K * 0.7 us: crossover near 3000 chunks (measured on B200, profiles/r2c_sweep.txt).
-  const bool use_sync = K <= sync_max_chunks();
+  const bool use_sync = K <= sync_max_chunks(G);
   DecodeCfg cfg;
   {
     const int rc = fill_decode_cfg(cfg, d_body, body_len, G, bits_mode, chunk, orig, d_out, (uint8_t*)d_ws, ws_bytes, use_sync);
@@ -525,7 +528,6 @@ int zipnn_b200_decompress_batch(const zipnn_b200_batch_item* items, int n, void*
   uint8_t* ws = (uint8_t*)d_ws;
   const size_t hdr = batch_header_bytes(n);
   if (ws_bytes < hdr) return ZIPNN_B200_E_CAPACITY;
-  const uint64_t sync_max = sync_max_chunks();
   std::vector<DecodeCfg> cfgs((size_t)n);
   std::vector<uint64_t> starts(3 * ((size_t)n + 1), 0);
   uint64_t* chunk_start = starts.data();
@@ -548,7 +550,7 @@ int zipnn_b200_decompress_batch(const zipnn_b200_batch_item* items, int n, void*
     if (it.orig == 0) continue;
     if (!it.d_body || !it.d_out || ((uintptr_t)it.d_out & 15)) return ZIPNN_B200_E_ARG;
     const uint64_t K = num_chunks(it.orig, it.chunk);
-    const bool small = K <= sync_max;
+    const bool small = K <= sync_max_chunks(it.num_buf);
     const int rc = fill_decode_cfg(cfgs[i], it.d_body, it.body_len, it.num_buf, it.bits_mode, it.chunk, it.orig, it.d_out, ws + at, slice, small);
     if (rc) return rc;
     ZB_CUDA(cudaMemsetAsync(ws + at, 0, kCtrlBytes, st));
