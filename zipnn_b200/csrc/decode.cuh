@@ -977,6 +977,14 @@ __device__ __forceinline__ void take16(const uint4& a, const uint4& b, uint32_t 
   for (int i = 0; i < 4; i++) out[i] = s4 ? u[i + 1] : u[i];
 }
 
+// The same with the word part of the shift (W = shift / 4) known at compile time: four funnel shifts, no selects.
+template <int W>
+__device__ __forceinline__ void take16_w(const uint4& a, const uint4& b, uint32_t bit_shift, uint32_t (&out)[4]) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = __funnelshift_r(w[i + W], w[i + W + 1], bit_shift);
+}
+
 // Un-rotate at plane level: the two top byte planes hold [sign|mant7] (lo) and [exponent] (hi) of every element;
 // the element's real top bytes are hi' = sign | exp >> 1, lo' = exp << 7 | mant7.
 // The fused kernel's tables hold the exponent bytes already rotated right by one (lut_symbol), E = ror8(exp), so
@@ -1265,33 +1273,57 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
         uint64_t row_out[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) row_out[r] = __shfl_sync(0xffffffffu, my_out, r * 4 + (lane >> 3)) + (uint64_t)(lane & 7) * 16;
-        for (uint32_t row = 0; row < rows_full; row++) {
+        // side_r0 is the same for every warp of the launch: the word part of the alignment shift is a 4-way switch
+        // around the row loop (four funnel shifts per iteration instead of seven shifts + nine selects)
+        const uint32_t bit_shift = (r0 & 3u) * 8u;
+        auto run_rows = [&](auto wtag) {
+          constexpr int W = decltype(wtag)::value;
+          for (uint32_t row = 0; row < rows_full; row++) {
 #pragma unroll
-          for (int tr = 0; tr < kTilesPerRow; tr++) {
-            const uint32_t t = row * (uint32_t)kTilesPerRow + (uint32_t)tr;
-            const uint32_t n = tiles_done + t;
-            __syncwarp();  // every lane has read tile t-1: its stage may be overwritten by tile t+1
-            if (lane == 0 && t + 1 < ntiles) issue_tile(t + 1);
-            mbar_wait(bar_s + 8u * (n & 1u), (n >> 1) & 1u);
-            const uint32_t my_row = side_tile_s<G>(S, n & 1u) + (uint32_t)lane * Geo::kTileRow;
-            uint4 blk[kTI + 1];
+            for (int tr = 0; tr < kTilesPerRow; tr++) {
+              const uint32_t t = row * (uint32_t)kTilesPerRow + (uint32_t)tr;
+              const uint32_t n = tiles_done + t;
+              __syncwarp();  // every lane has read tile t-1: its stage may be overwritten by tile t+1
+              if (lane == 0 && t + 1 < ntiles) issue_tile(t + 1);
+              mbar_wait(bar_s + 8u * (n & 1u), (n >> 1) & 1u);
+              const uint32_t my_row = side_tile_s<G>(S, n & 1u) + (uint32_t)lane * Geo::kTileRow;
+              uint4 blk[kTI + 1];
 #pragma unroll
-            for (int q = 0; q <= kTI; q++) blk[q] = lds_u128(my_row + 16u * (uint32_t)q);
+              for (int q = 0; q <= kTI; q++) blk[q] = lds_u128(my_row + 16u * (uint32_t)q);
 #pragma unroll
-            for (int ki = 0; ki < kTI; ki++) {
-              uint32_t pl[G][4];
-              decode16(b, lut, pl[G - 1]);
-              take16(blk[ki], blk[ki + 1], r0, pl[0]);
-              emit_elements<G>(pl, rot, stage, lane, (tr * kTI + ki) * G);
+              for (int ki = 0; ki < kTI; ki++) {
+                uint32_t pl[G][4];
+                decode16(b, lut, pl[G - 1]);
+                take16_w<W>(blk[ki], blk[ki + 1], bit_shift, pl[0]);
+                if (tr == 0 && ki == 0 && store_pending) {  // the previous row's bulk store still reads the stage
+                  if (lane == 0) tma_store_wait_read();
+                  store_pending = false;
+                  __syncwarp();
+                }
+                emit_elements<G>(pl, rot, stage, lane, (tr * kTI + ki) * G);
+              }
+            }
+            if (out_tma) {  // the 32 rows leave with one bulk tensor store (no LSU instruction)
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) tma_store_2d(&maps.out, stage_s, row * 128u, y0);
+              store_pending = true;
+            } else {
+              __syncwarp();
+#pragma unroll
+              for (int r = 0; r < 8; r++) {
+                const uint4 v = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
+                *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
+              }
+              __syncwarp();
             }
           }
-          __syncwarp();
-#pragma unroll
-          for (int r = 0; r < 8; r++) {
-            const uint4 v = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
-            *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
-          }
-          __syncwarp();
+        };
+        switch (r0 >> 2) {
+          case 0: run_rows(std::integral_constant<int, 0>{}); break;
+          case 1: run_rows(std::integral_constant<int, 1>{}); break;
+          case 2: run_rows(std::integral_constant<int, 2>{}); break;
+          default: run_rows(std::integral_constant<int, 3>{}); break;
         }
         tiles_done += ntiles;
         if (live && !window_exact(b)) atomicOr(&cfg.ctrl->error, kErrCorrupt);
