@@ -318,7 +318,9 @@ __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
     // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above qm + 4 (the container and
     // `next` hold everything from there up; later reads are at qm and below)
     if (b.fetch >= 16 + b.floor_off && f + (kRingBytes - 4) >= b.qm) {
-      cp_async16_s(b.ring_s | (f & (kRingBytes - 16)), b.gbase + f);  // f is a multiple of 16; the ring is ring-size aligned
+      uint64_t src;  // gbase + f as ONE instruction (IMAD.WIDE.U32) instead of an add with carry
+      asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(src) : "r"(f), "l"((uint64_t)(uintptr_t)b.gbase));
+      cp_async16_s(b.ring_s | (f & (kRingBytes - 16)), reinterpret_cast<const void*>((uintptr_t)src));  // f is a multiple of 16; the ring is ring-size aligned
       b.fetch = f;
     }
   }
@@ -995,10 +997,11 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m
   asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
   return d;
 }
-__device__ __forceinline__ void unrotate_planes_pre(uint32_t& lo, uint32_t& hi) {
+// m = 0x80808080 for a rotated type, 0 otherwise (then hi = e, lo = sm: nothing happens, without a branch)
+__device__ __forceinline__ void unrotate_planes_pre(uint32_t& lo, uint32_t& hi, uint32_t m) {
   const uint32_t sm = lo, e = hi;
-  hi = bitselect(sm, e, 0x80808080u);
-  lo = bitselect(e, sm, 0x80808080u);
+  hi = bitselect(sm, e, m);
+  lo = bitselect(e, sm, m);
 }
 
 // Output rows.  A lane produces 16*G bytes per iteration, 64 KiB away from its neighbours'
@@ -1014,15 +1017,13 @@ __device__ __forceinline__ uint4* stage_unit(uint8_t (*stage)[128], int row, int
 // Planes of 16 elements (pl[g][q] = bytes 4q..4q+3 of plane g) -> un-rotated, interleaved, into
 // units [unit0, unit0 + G) of the lane's stage row.
 template <int G>
-__device__ __forceinline__ void emit_elements(uint32_t (&pl)[G][4], bool rot, uint8_t (*stage)[128], int lane, int unit0) {
+__device__ __forceinline__ void emit_elements(uint32_t (&pl)[G][4], uint32_t rot_mask, uint8_t (*stage)[128], int lane, int unit0) {
   if (G == 1) {
     *stage_unit(stage, lane, unit0) = make_uint4(pl[0][0], pl[0][1], pl[0][2], pl[0][3]);
     return;
   }
-  if (rot) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) unrotate_planes_pre(pl[(G - 2) % G][q], pl[G - 1][q]);  // the tables hold ror8(symbol)
-  }
+  for (int q = 0; q < 4; q++) unrotate_planes_pre(pl[(G - 2) % G][q], pl[G - 1][q], rot_mask);  // the tables hold ror8(symbol)
   uint32_t w[4 * G];
   if (G == 2) {
 #pragma unroll
@@ -1072,7 +1073,7 @@ __device__ __forceinline__ void fused_iteration(BitWindow& b, const LUT& lut, Si
 #pragma unroll
     for (int g = 0; g < G - 1; g++) take16(side[g].a, side[g].b, side[g].shift, pl[g]);
   }
-  emit_elements<G>(pl, rot, stage, lane, unit0);
+  emit_elements<G>(pl, rot ? 0x80808080u : 0u, stage, lane, unit0);
   if (G > 1) {
 #pragma unroll
     for (int g = 0; g < G - 1; g++) {
@@ -1110,6 +1111,7 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
   uint8_t (*const stage)[128] = S.stage();
   const uint32_t stage_s = S.base_s + S.stage_off;
   const bool rot = (cfg.bits_mode == 1) && (G > 1);
+  const uint32_t rot_mask = rot ? 0x80808080u : 0u;
   const uint4* hi_block = reinterpret_cast<const uint4*>(((uintptr_t)(cfg.body + cfg.body_len) - 1) & ~(uintptr_t)15);
 
   for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -1295,28 +1297,18 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
                 uint32_t pl[G][4];
                 decode16(b, lut, pl[G - 1]);
                 take16_w<W>(blk[ki], blk[ki + 1], bit_shift, pl[0]);
-                if (tr == 0 && ki == 0 && store_pending) {  // the previous row's bulk store still reads the stage
-                  if (lane == 0) tma_store_wait_read();
-                  store_pending = false;
-                  __syncwarp();
-                }
-                emit_elements<G>(pl, rot, stage, lane, (tr * kTI + ki) * G);
+                emit_elements<G>(pl, rot_mask, stage, lane, (tr * kTI + ki) * G);
               }
             }
-            if (out_tma) {  // the 32 rows leave with one bulk tensor store (no LSU instruction)
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) tma_store_2d(&maps.out, stage_s, row * 128u, y0);
-              store_pending = true;
-            } else {
-              __syncwarp();
+            // (a bulk tensor store of the 32 rows instead of these 8 x (LDS.128 + STG.128) was measured here too:
+            //  7.35 ms against 7.35 -- the fence and the wait for the store's reads cost what the LSU work saves)
+            __syncwarp();
 #pragma unroll
-              for (int r = 0; r < 8; r++) {
-                const uint4 v = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
-                *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
-              }
-              __syncwarp();
+            for (int r = 0; r < 8; r++) {
+              const uint4 v = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
+              *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
             }
+            __syncwarp();
           }
         };
         switch (r0 >> 2) {
