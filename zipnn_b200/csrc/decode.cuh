@@ -299,10 +299,11 @@ struct BitWindow {
                          // address of that word is ring_s | (qm & 60): one LOP3, so no second pointer has to be kept
   uint32_t next;         // the word at q - 4
   uint32_t ring_s;       // shared-space address of the ring (64-byte aligned)
-  uint32_t fetch;        // byte offset (from gbase) of the lowest 16-byte block already requested
+  uint32_t fetch48;      // 48 + byte offset (from gbase) of the lowest 16-byte block already requested: biased so that
+                         // "the next block's ring slot is free" is the single compare fetch48 > qm (ring_top_up)
   uint32_t start_bit;    // bit offset (from gbase) of the first stream bit (exact-consumption check)
-  const uint8_t* gbase;  // 128-byte aligned global address the offsets are relative to
-  uint32_t floor_off;    // do not request blocks below this offset (start of the stream buffer)
+  const uint8_t* gsrc;   // (the 64-byte aligned global address the offsets are relative to) - 64: block source = gsrc + fetch48
+  uint32_t floor64;      // 64 + the offset below which no block may be requested (start of the stream buffer)
   const uint8_t* ring;
 };
 
@@ -314,14 +315,14 @@ __device__ __forceinline__ uint32_t ring_word(const uint8_t* ring, uint32_t off)
 __device__ __forceinline__ void ring_top_up(BitWindow& b, int maxn) {
 #pragma unroll 2
   for (int i = 0; i < maxn; i++) {
-    const uint32_t f = b.fetch - 16;
-    // block [f, f+16) replaces ring bytes [f+64, f+80): free once they lie at or above qm + 4 (the container and
-    // `next` hold everything from there up; later reads are at qm and below)
-    if (b.fetch >= 16 + b.floor_off && f + (kRingBytes - 4) >= b.qm) {
-      uint64_t src;  // gbase + f as ONE instruction (IMAD.WIDE.U32) instead of an add with carry
-      asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(src) : "r"(f), "l"((uint64_t)(uintptr_t)b.gbase));
-      cp_async16_s(b.ring_s | (f & (kRingBytes - 16)), reinterpret_cast<const void*>((uintptr_t)src));  // f is a multiple of 16; the ring is ring-size aligned
-      b.fetch = f;
+    // The next block is [f, f + 16) with f = fetch - 16 = fetch48 - 64.  It replaces ring bytes [f + 64, f + 80): free
+    // once they lie at or above qm + 4 (the container and `next` hold everything from there up; later reads are at
+    // qm and below), i.e. f + 60 >= qm, i.e. fetch48 > qm (both are multiples of 4).
+    if (b.fetch48 >= b.floor64 && b.fetch48 > b.qm) {
+      uint64_t src;  // gsrc + fetch48 as ONE instruction (IMAD.WIDE.U32) instead of an add with carry
+      asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(src) : "r"(b.fetch48), "l"((uint64_t)(uintptr_t)b.gsrc));
+      cp_async16_s(b.ring_s | (b.fetch48 & (kRingBytes - 16)), reinterpret_cast<const void*>((uintptr_t)src));  // (f & 48) == (fetch48 & 48)
+      b.fetch48 -= 16;
     }
   }
 }
@@ -356,9 +357,10 @@ __device__ __forceinline__ void window_refill(BitWindow& b) {
 __device__ __forceinline__ uint32_t window_frame(BitWindow& b, const uint8_t* s, const uint8_t* lo, uint8_t* ring) {
   b.ring = ring;
   b.ring_s = (uint32_t)__cvta_generic_to_shared(ring);
-  b.gbase = reinterpret_cast<const uint8_t*>(((uintptr_t)s & ~(uintptr_t)(kRingBytes - 1)) - kRingBytes);
-  b.floor_off = (b.gbase < lo) ? (uint32_t)(((uintptr_t)lo - (uintptr_t)b.gbase + 15) & ~(uintptr_t)15) : 0u;
-  const uint32_t s_off = (uint32_t)((uintptr_t)s - (uintptr_t)b.gbase);
+  const uint8_t* gbase = reinterpret_cast<const uint8_t*>(((uintptr_t)s & ~(uintptr_t)(kRingBytes - 1)) - kRingBytes);
+  b.gsrc = gbase - 64;
+  b.floor64 = 64u + ((gbase < lo) ? (uint32_t)(((uintptr_t)lo - (uintptr_t)gbase + 15) & ~(uintptr_t)15) : 0u);
+  const uint32_t s_off = (uint32_t)((uintptr_t)s - (uintptr_t)gbase);
   b.start_bit = 8u * s_off;
   return s_off;
 }
@@ -368,7 +370,7 @@ __device__ __forceinline__ void window_seek(BitWindow& b, uint32_t mark) {
   const uint32_t q = (top_byte & ~3u) - 4u;
   b.qm = q - 8u;
   b.s = 53 - (int32_t)(8u * (q + 8u) - mark);  // 1..32 bits lie above the first unread bit
-  b.fetch = (top_byte & ~15u) + 16;
+  b.fetch48 = (top_byte & ~15u) + 16 + 48;
   ring_top_up(b, (int)(kRingBytes / 16));
   cp_async_commit();
   cp_async_wait<0>();
@@ -1243,10 +1245,10 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
     // (a lane that drops out here only happens on a corrupt stream; `regular` groups keep going with the
     //  lane decoding garbage from its zeroed window -- the error bit is already set, the output is discarded)
     if (regular && !live) {
-      b.cont = 0; b.s = 53; b.qm = 0; b.next = 0; b.fetch = 0; b.floor_off = 0xffffffffu; b.start_bit = 0;
+      b.cont = 0; b.s = 53; b.qm = 0; b.next = 0; b.fetch48 = 0; b.floor64 = 0xffffffffu; b.start_bit = 0;
       b.ring = S.ring(lane);
       b.ring_s = (uint32_t)__cvta_generic_to_shared(b.ring);
-      b.gbase = cfg.body;
+      b.gsrc = cfg.body;
     }
 
     const uint32_t rows_full = (seg >> 4) / kIters;
@@ -1270,11 +1272,13 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
           tma_load_2d(side_tile_s<G>(S, st), &maps.side[0], 16u * (uint32_t)kTI * t, y0, bar_s + 8u * st);
         };
         if (lane == 0 && ntiles) issue_tile(0);
-        // the 8 stage rows this lane writes out each round: row r*4 + lane/8, 16-byte unit lane%8
-        const uint64_t my_out = (uint64_t)(uintptr_t)(out + c * (uint64_t)cfg.chunk + (uint64_t)out_off * G);
-        uint64_t row_out[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) row_out[r] = __shfl_sync(0xffffffffu, my_out, r * 4 + (lane >> 3)) + (uint64_t)(lane & 7) * 16;
+        // The 8 stage rows this lane writes out each round are rows 4r + lane/8 = stream lane/8 of chunk slot r, 16-byte
+        // unit lane%8: with full chunks (this path) they lie at flush_ptr + r * chunk, so ONE pointer that moves on by
+        // 128 per row serves all eight stores -- as immediate offsets for the reference's default chunk size.
+        uint8_t* flush_ptr = out + (grp * (uint64_t)kDecItemsPerWarp) * (uint64_t)cfg.chunk + (uint64_t)((uint32_t)(lane >> 3) * seg) * G +
+                             (uint32_t)(lane & 7) * 16u;
+        const uint32_t chunk_b = cfg.chunk;
+        const bool chunk_256k = chunk_b == 262144u;
         // side_r0 is the same for every warp of the launch: the word part of the alignment shift is a 4-way switch
         // around the row loop (four funnel shifts per iteration instead of seven shifts + nine selects)
         const uint32_t bit_shift = (r0 & 3u) * 8u;
@@ -1303,11 +1307,14 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
             // (a bulk tensor store of the 32 rows instead of these 8 x (LDS.128 + STG.128) was measured here too:
             //  7.35 ms against 7.35 -- the fence and the wait for the store's reads cost what the LSU work saves)
             __syncwarp();
+            if (chunk_256k) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-              const uint4 v = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
-              *reinterpret_cast<uint4*>((uintptr_t)(row_out[r] + (uint64_t)row * 128)) = v;
+              for (int r = 0; r < 8; r++) *reinterpret_cast<uint4*>(flush_ptr + (size_t)r * 262144u) = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
+            } else {
+#pragma unroll
+              for (int r = 0; r < 8; r++) *reinterpret_cast<uint4*>(flush_ptr + (size_t)r * chunk_b) = *stage_unit(stage, r * 4 + (lane >> 3), lane & 7);
             }
+            flush_ptr += 128;
             __syncwarp();
           }
         };
