@@ -1138,9 +1138,28 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
       uint8_t* weights = S.weights(slot);
       const bool builder = active && stream == 0;
       int nsym = 0;
+      // The table description (<= 128 bytes: 1 + 127 of tANS-coded weights, or 1 + 64 of 4-bit weights,
+      // huf_compress.c:140-167) goes to shared memory first, 16-byte blocks by the chunk's four lanes: the parser is
+      // serial and reads it a byte at a time -- from global memory that was a DRAM / L2 round trip per pair of
+      // weights (2 % of the kernel's samples sat on it).  The tail pool is free until the fill.
+      constexpr uint32_t kHdrSlot = 176;  // 15 bytes of misalignment + 128 + the parser's 4-byte peeks, in 16-byte blocks
+      uint8_t* hdr = reinterpret_cast<uint8_t*>(S.tail()) + kHdrSlot * (uint32_t)slot;
+      const uint8_t* tsrc = cfg.body + d.src_off;
+      const uint32_t mis = (uint32_t)((uintptr_t)tsrc & 15u);
+      if (active) {
+        const uint8_t* body_end = cfg.body + cfg.body_len;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const int blk = stream + 4 * q;
+          const uint8_t* g = tsrc - mis + 16 * blk;
+          if (blk < (int)(kHdrSlot / 16) && g < body_end) *reinterpret_cast<uint4*>(hdr + 16 * blk) = ldg128(reinterpret_cast<const uint4*>(g));
+        }
+      }
+      __syncwarp();
       if (builder) {
         FseDecSmall& D = *reinterpret_cast<FseDecSmall*>(&stage[4 * slot][0]);
-        hsize = huf_read_weights(weights, &nsym, &lg, cfg.body + d.src_off, d.src_len, D);
+        const uint32_t avail = kHdrSlot - mis;
+        hsize = huf_read_weights(weights, &nsym, &lg, hdr + mis, d.src_len < avail ? d.src_len : avail, D);
         if (hsize >= 0) {
           // (the tANS scratch D is dead once the weights are out: its first 32 bytes carry the class starts to the fill)
           x_long = PB == 0 ? lut2_tail_size(weights, nsym, lg) : lut_tail_size(weights, nsym, lg, PB, reinterpret_cast<uint16_t*>(&stage[4 * slot][0]));
