@@ -418,20 +418,21 @@ struct LutTwo {
   uint32_t prim_s;  // shared-space byte address of the 256-entry primary
   uint32_t tail_s;  // ... of the x_long-entry tail (32-bit shared addresses: a generic pointer makes
                     // the compiler rebuild the shared window base for every lookup)
-  uint32_t x_long;
+  uint32_t hi_mask;  // 0x7FF & ~(x_cut - 1): the tail serves every index below x_cut (see LutCol::get)
   __device__ __forceinline__ int32_t get(uint32_t x) const {
-    // idx < x_long ? tail_s + 2 * idx : ((x >> 2) & 0x1FE) | prim_s -- one load, address selected (see LutCol for
-    // why this is PTX); every primary is 512-byte aligned
+    // (idx & hi_mask) == 0 ? tail_s + 2 * idx : ((x >> 2) & 0x1FE) | prim_s -- one load, address selected, the test
+    // one LOP3 with a predicate result (see LutCol for why this is PTX); every primary is 512-byte aligned
     int32_t v;
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 i, a;\n\t"
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 i, a, t;\n\t"
+        "and.b32 t, %1, %4;\n\t"
+        "setp.eq.u32 p, t, 0;\n\t"
         "and.b32 i, %1, 0x7FF;\n\t"
         "shr.u32 a, %1, 2;\n\t"
         "lop3.b32 a, a, 0x1FE, %2, 0xEA;\n\t"
-        "setp.lt.u32 p, i, %4;\n\t"
         "@p mad.lo.u32 a, i, 2, %3;\n\t"
         "ld.shared.s16 %0, [a];\n\t}"
         : "=r"(v)
-        : "r"(x), "r"(prim_s), "r"(tail_s), "r"(x_long));
+        : "r"(x), "r"(prim_s), "r"(tail_s), "r"(hi_mask));
     return v;
   }
 };
@@ -629,8 +630,9 @@ __device__ __forceinline__ void fill_lut(uint16_t* lut, const uint8_t* weights, 
   }
 }
 
-// Two-level table, step 1: the tail size (index bound of the codes longer than 8 bits) in the
-// 11-bit index space, or -1 when the table log exceeds 11 (the caller demotes the chunk).
+// Two-level table, step 1: the tail size in the 11-bit index space = x_cut, the power of two (>= 8) at or above the
+// index bound x_long of the codes longer than 8 bits (fp16 / fp8 planes: x_long ~ 80 .. 160), or -1 when the table log
+// exceeds 11 (the caller demotes the chunk).
 __device__ __forceinline__ int lut2_tail_size(const uint8_t* weights, int nsym, int lg) {
   if (lg > kDecLutLog) return -1;
   uint32_t cnt[kHufLogMax + 2];
@@ -642,11 +644,14 @@ __device__ __forceinline__ int lut2_tail_size(const uint8_t* weights, int nsym, 
     at += (cnt[w] << (w - 1)) << (kDecLutLog - lg);
     if (lg + 1 - w > 8) x_long = at;
   }
-  return (int)x_long;
+  uint32_t x_cut = 8;
+  while (x_cut < x_long) x_cut <<= 1;
+  return (int)x_cut;
 }
 
-// Step 2: fill the 256-entry primary and the x_long-entry tail.
-__device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const uint8_t* weights, int nsym, int lg, bool pre_rot) {
+// Step 2: fill the 256-entry primary and the x_cut-entry tail (the codes longer than 8 bits and whatever of the shorter
+// ones lies below x_cut).
+__device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const uint8_t* weights, int nsym, int lg, bool pre_rot, uint32_t x_cut) {
   uint32_t cnt[kHufLogMax + 2];
 #pragma unroll
   for (int i = 0; i < kHufLogMax + 2; i++) cnt[i] = 0;
@@ -672,6 +677,10 @@ __device__ __forceinline__ void fill_lut2(uint16_t* prim, uint16_t* tail, const 
     } else {
       const uint32_t p0 = u >> 3, pn = span >> 3;
       for (uint32_t q = 0; q < pn; q++) prim[p0 + q] = e;
+      if (u < x_cut) {
+        const uint32_t end = u + span < x_cut ? u + span : x_cut;
+        for (uint32_t q = u; q < end; q++) tail[q] = e;
+      }
     }
   }
 }
@@ -1180,7 +1189,7 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
       }
       if (builder) {
         if (hsize >= 0) {
-          if (PB == 0) fill_lut2(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + 256 * slot, S.tail() + tail_at, weights, nsym, lg, rot);
+          if (PB == 0) fill_lut2(reinterpret_cast<uint16_t*>(S.raw + S.table_off) + 256 * slot, S.tail() + tail_at, weights, nsym, lg, rot, (uint32_t)x_long);
         } else {
           // Not an error yet: a table that needs the big scratch, a long tail or log 12, or a
           // corrupt one.  Hand the chunk to the general kernels, which decide.
@@ -1236,11 +1245,7 @@ __global__ void __launch_bounds__(32, G == 4 ? 12 : ZB_FUSED_MIN_BLOCKS) k_huf_d
       lut.col_s = S.base_s + S.table_off + 2u * (uint32_t)lane;
     }
     lut.tail_s = S.base_s + S.tail_off + 2u * tail_at;
-    if constexpr (PB == 0) {
-      lut.x_long = (uint32_t)x_long;
-    } else {
-      lut.hi_mask = 0x7FFu & ~((uint32_t)x_long - 1u);   // x_long holds x_cut here (lut_tail_size)
-    }
+    lut.hi_mask = 0x7FFu & ~((uint32_t)x_long - 1u);   // x_long holds x_cut here (lut_tail_size / lut2_tail_size)
 
     // ---- which way do the other planes and the output travel?  (warp-uniform) ----
     // Bulk tensor copies need all 32 lanes live on full chunks and every other plane stored raw at its
