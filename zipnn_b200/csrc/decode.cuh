@@ -407,7 +407,8 @@ struct LutFull {
 // Two-level table in an 11-bit index space (shorter table logs are replicated into it):
 // codes of <= 8 bits resolve in a 256-entry primary indexed by the top 8 bits; longer codes
 // sit at the bottom of the canonical order (index < x_long) and resolve in a tail table
-// indexed by all 11 bits (read only by the lanes that need it).
+// indexed by all 11 bits (read only by the lanes that need it); the tail serves every index below
+// x_cut = the power of two at or above x_long, so that the test is one instruction (LutCol::get).
 // 1 KiB per block instead of 4 KiB: three times as many bitstreams resident per SM.
 __device__ __forceinline__ int32_t lds_s16(uint32_t saddr) {
   int32_t v;  // sign-extended: byte 1 of an entry is minus the code length
@@ -416,7 +417,7 @@ __device__ __forceinline__ int32_t lds_s16(uint32_t saddr) {
 }
 struct LutTwo {
   uint32_t prim_s;  // shared-space byte address of the 256-entry primary
-  uint32_t tail_s;  // ... of the x_long-entry tail (32-bit shared addresses: a generic pointer makes
+  uint32_t tail_s;  // ... of the x_cut-entry tail (32-bit shared addresses: a generic pointer makes
                     // the compiler rebuild the shared window base for every lookup)
   uint32_t hi_mask;  // 0x7FF & ~(x_cut - 1): the tail serves every index below x_cut (see LutCol::get)
   __device__ __forceinline__ int32_t get(uint32_t x) const {
