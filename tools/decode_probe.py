@@ -17,7 +17,6 @@ CONFIGS = [
     {"ZIPNN_B200_SMEM_PAD": "3072"},
     {"ZIPNN_B200_SMEM_PAD": "6144"},
     {"ZIPNN_B200_SMEM_PAD": "12288"},
-    {"ZIPNN_B200_TMA": "3"},            # side tiles AND the output rows by bulk tensor stores
     {"ZIPNN_B200_TMA": "0"},            # side plane through cp.async slots instead of bulk tensor tiles
     {"ZIPNN_B200_TMA": "1"},            # ... and the output rows by bulk tensor stores
     {"ZIPNN_B200_GRID_MODE": "0"},      # persistent grid
