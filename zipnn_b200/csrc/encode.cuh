@@ -76,11 +76,9 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   HistSmem<G>& S = *reinterpret_cast<HistSmem<G>*>(smem_raw);
   constexpr int R = HistCfg<G>::R;
-  constexpr int kShift = HistCfg<G>::kShift;
-  constexpr uint32_t kBinMask = 0xFFu << kShift;
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t col_bytes = (uint32_t)(lane % R) * 4;
-  unsigned char* const rep_base = reinterpret_cast<unsigned char*>(&S.rep[0][0][0]);
+  unsigned char* const col_p = reinterpret_cast<unsigned char*>(&S.rep[0][0][0]) + col_bytes;  // rep[0][0][lane % R]
   for (int i = tid; i < G * 256 * R; i += kEncThreads) (&S.rep[0][0][0])[i] = 0;
   __syncthreads();
   for (uint64_t c = blockIdx.x; c < K; c += gridDim.x) {
@@ -121,11 +119,12 @@ __global__ void __launch_bounds__(kEncThreads) k_encode_hist(const uint8_t* __re
                 if (rot_words) w[i] = rot_word<G>(w[i]);
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                  // byte b of the word -> (bin << kShift) | column, without extracting the byte
-                  const int sh = 8 * b - kShift;
-                  const uint32_t t = sh >= 0 ? (w[i] >> sh) : (w[i] << (-sh));
-                  const uint32_t off = (t & kBinMask) | col_bytes;
-                  atomicAdd(reinterpret_cast<uint32_t*>(rep_base + ((4 * i + b) % G) * (256 * R * 4) + off), inc);
+                  // byte b of the word -> address of its counter in THREE instructions: extract (PRMT with zeros),
+                  // bin * (R * 4) + this lane's column (one multiply-add on the FMA pipe), shared-memory reduction
+                  // with the plane as an immediate offset.  (Shift, mask | column, add the array base, ATOMS took four,
+                  // and the kernel is bound by instruction issue: profiles/r2p_encode_16GiB.summary.txt)
+                  const uint32_t byte = __byte_perm(w[i], 0u, 0x4440u | (uint32_t)b);
+                  atomicAdd(reinterpret_cast<uint32_t*>(col_p + ((4 * i + b) % G) * (256 * R * 4) + byte * (uint32_t)(R * 4)), inc);
                 }
               }
             }
